@@ -1,0 +1,584 @@
+// b2_api.cu — the C ABI (include/b2slam.h) over the kernels of this directory.
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+#include "b2_common.cuh"
+
+namespace b2 {
+
+int set_error(Context* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->last_error = buf;
+    return code;
+}
+
+void* ws_get(Context* c, int slot, size_t bytes) {
+    DevBuf& b = c->ws[slot];
+    if (bytes == 0) bytes = 16;
+    if (b.cap >= bytes) return b.p;
+    size_t want = bytes + bytes / 4;  // headroom so slowly growing inputs do not reallocate every call
+    want = (want + 255) & ~(size_t)255;
+    if (b.p) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        set_error(c, B2_ERR_CUDA, "cudaMalloc(%zu bytes) for workspace slot %d failed: %s", want, slot,
+                  cudaGetErrorString(e));
+        b.p = nullptr;
+        return nullptr;
+    }
+    b.cap = want;
+    return b.p;
+}
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__global__ void pack_xyz_kernel(const float* __restrict__ xyz, int n, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f);
+}
+
+__global__ void unpack_xyz_kernel(const float4* __restrict__ in, int n, float* __restrict__ xyz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    xyz[3 * i] = p.x;
+    xyz[3 * i + 1] = p.y;
+    xyz[3 * i + 2] = p.z;
+}
+
+// generic_point_cloud_processor.py:93-108
+__global__ void project_kernel(const float* __restrict__ rec, int n, double fx, double fy, double cx, double cy,
+                               int numpy2, float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float xp = rec[3 * i], yp = rec[3 * i + 1], z = rec[3 * i + 2];
+    float x, y;
+    if (numpy2) {
+        x = __fdiv_rn(__fmul_rn(__fsub_rn(xp, (float)cx), z), (float)fx);
+        y = __fdiv_rn(__fmul_rn(__fsub_rn(yp, (float)cy), z), (float)fy);
+    } else {
+        x = (float)ddiv(dmul(dsub((double)xp, cx), (double)z), fx);
+        y = (float)ddiv(dmul(dsub((double)yp, cy), (double)z), fy);
+    }
+    out[i] = make_float4(x, y, z, 0.f);
+}
+
+__global__ void transform_kernel(const float4* __restrict__ in, int n, const double* __restrict__ T,
+                                 float4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = in[i];
+    const D3 q = xform_strict(T, (double)p.x, (double)p.y, (double)p.z);
+    out[i] = make_float4((float)q.x, (float)q.y, (float)q.z, p.w);
+}
+
+__global__ void copy_pose_kernel(const IcpResultDev* __restrict__ res, double* __restrict__ pose) {
+    if (threadIdx.x < 16) pose[threadIdx.x] = res->T[threadIdx.x];
+}
+
+int check_T(Context* c, const double* T, const char* what) {
+    if (!T) return B2_OK;
+    for (int i = 0; i < 16; ++i)
+        if (!std::isfinite(T[i])) return set_error(c, B2_ERR_INVALID, "%s: transform has non-finite entries", what);
+    if (T[12] != 0.0 || T[13] != 0.0 || T[14] != 0.0 || T[15] != 1.0)
+        return set_error(c, B2_ERR_INVALID, "%s: last row of the transform must be (0,0,0,1)", what);
+    return B2_OK;
+}
+
+// Upload 16 doubles to the small device scratch area (slot k of WS_MISC).
+int upload_T(Context* c, const double* T, int k, double** dev) {
+    B2_WS(c, misc, double, WS_MISC, sizeof(double) * 16 * 16);
+    double* d = misc + 16 * k;
+    B2_CUDA_OK(c, cudaMemcpyAsync(d, T, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
+    *dev = d;
+    return B2_OK;
+}
+
+// Read and clear the sticky device status word (synchronises).
+int check_status(Context* c) {
+    int* h = (int*)c->host_mailbox + 640;
+    B2_CUDA_OK(c, cudaMemcpyAsync(h, c->dev_status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    const int st = *h;
+    if (st == 0) return B2_OK;
+    B2_CUDA_OK(c, cudaMemsetAsync(c->dev_status, 0, sizeof(int), c->stream));
+    switch (st) {
+        case B2_ERR_KEY_RANGE:
+            return set_error(c, st, "voxel / cell index out of range (int32 voxel index, packed key width or "
+                                    "radix pass budget exceeded)");
+        case B2_ERR_CAPACITY:
+            return set_error(c, st, "resident map is full: raise capacity_cells in b2_map_init");
+        default:
+            return set_error(c, st, "device-side failure %d", st);
+    }
+}
+
+IcpParams to_internal(const b2_icp_params* p) {
+    IcpParams q;
+    q.max_corr = p->max_correspondence_distance;
+    q.max_iter = p->max_iteration;
+    q.rel_fitness = p->relative_fitness;
+    q.rel_rmse = p->relative_rmse;
+    q.mode = p->mode;
+    return q;
+}
+
+int check_params(Context* c, const b2_icp_params* p) {
+    if (!p) return set_error(c, B2_ERR_INVALID, "icp params are NULL");
+    if (!(p->max_correspondence_distance > 0.0)) return set_error(c, B2_ERR_INVALID, "max_correspondence_distance must be > 0");
+    if (p->max_iteration < 0) return set_error(c, B2_ERR_INVALID, "max_iteration must be >= 0");
+    if (p->mode != B2_ICP_POINT_TO_POINT && p->mode != B2_ICP_POINT_TO_PLANE)
+        return set_error(c, B2_ERR_INVALID, "unknown estimation mode %d", p->mode);
+    return B2_OK;
+}
+
+void fill_result(const IcpResultDev* r, b2_icp_result* out) {
+    std::memcpy(out->transformation, r->T, sizeof(double) * 16);
+    out->fitness = r->fitness;
+    out->inlier_rmse = r->rmse;
+    out->iterations = r->iterations;
+    out->n_correspondences = r->n_corr;
+}
+
+struct HintGuard {  // widen the radix pass budget for the duration of a call
+    Context* c;
+    int saved;
+    HintGuard(Context* ctx, int h) : c(ctx), saved(ctx->sort_passes_hint) {
+        if (h > c->sort_passes_hint) c->sort_passes_hint = h;
+    }
+    ~HintGuard() { c->sort_passes_hint = saved; }
+};
+
+}  // namespace
+}  // namespace b2
+
+using namespace b2;
+
+static_assert(sizeof(b2_icp_result) == sizeof(IcpResultDev), "result layouts must match");
+
+#define CTX(h)                               \
+    Context* c = reinterpret_cast<Context*>(h); \
+    if (!c) return B2_ERR_INVALID;           \
+    cudaSetDevice(c->device)
+
+// A sort whose key range does not fit the current radix pass budget reports KEY_RANGE once;
+// retry the whole call with the full 8-pass budget before giving up.
+#define B2_RETRY_WIDE(c, body)                                          \
+    do {                                                                \
+        int _rc = (body);                                               \
+        if (_rc == B2_ERR_KEY_RANGE && (c)->sort_passes_hint < 8) {     \
+            (c)->sort_passes_hint = 8;                                  \
+            _rc = (body);                                               \
+        }                                                               \
+        return _rc;                                                     \
+    } while (0)
+
+extern "C" {
+
+const char* b2_version(void) { return "b2slam 0.1 (sm_100a)"; }
+
+int b2_create(int device, b2_handle* out) {
+    if (!out) return B2_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return B2_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
+    Context* c = new Context();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return B2_ERR_CUDA;
+    }
+    c->own_stream = true;
+    if (cudaMalloc(&c->dev_status, sizeof(int)) != cudaSuccess ||
+        cudaMemset(c->dev_status, 0, sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc(&c->host_mailbox, 4096, cudaHostAllocDefault) != cudaSuccess) {
+        delete c;
+        return B2_ERR_CUDA;
+    }
+    *out = reinterpret_cast<b2_handle>(c);
+    return B2_OK;
+}
+
+int b2_destroy(b2_handle h) {
+    CTX(h);
+    cudaStreamSynchronize(c->stream);
+    map_free(c);
+    for (auto& b : c->ws)
+        if (b.p) cudaFree(b.p);
+    cudaFree(c->dev_status);
+    cudaFreeHost(c->host_mailbox);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B2_OK;
+}
+
+const char* b2_last_error(b2_handle h) {
+    Context* c = reinterpret_cast<Context*>(h);
+    return c ? c->last_error.c_str() : "invalid handle";
+}
+
+int b2_set_stream(b2_handle h, void* cuda_stream) {
+    CTX(h);
+    cudaStreamSynchronize(c->stream);
+    if (cuda_stream) {
+        if (c->own_stream) cudaStreamDestroy(c->stream);
+        c->stream = (cudaStream_t)cuda_stream;
+        c->own_stream = false;
+    } else if (!c->own_stream) {
+        B2_CUDA_OK(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return B2_OK;
+}
+
+int b2_synchronize(b2_handle h) {
+    CTX(h);
+    B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return check_status(c);
+}
+
+unsigned long long b2_launch_count(b2_handle h) {
+    Context* c = reinterpret_cast<Context*>(h);
+    return c ? c->launches : 0;
+}
+
+int b2_pack_xyz(b2_handle h, const float* xyz, int n, int src_on_host, float* out_xyzw_dev) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!xyz || !out_xyzw_dev))) return set_error(c, B2_ERR_INVALID, "b2_pack_xyz: bad arguments");
+    if (n == 0) return B2_OK;
+    const float* src = xyz;
+    if (src_on_host) {
+        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        src = stage;
+    }
+    pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(src, n, (float4*)out_xyzw_dev);
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
+
+int b2_unpack_xyz(b2_handle h, const float* xyzw_dev, int n, float* out_xyz, int dst_on_host) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!xyzw_dev || !out_xyz))) return set_error(c, B2_ERR_INVALID, "b2_unpack_xyz: bad arguments");
+    if (n == 0) return B2_OK;
+    float* dst = out_xyz;
+    if (dst_on_host) {
+        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+        dst = stage;
+    }
+    unpack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>((const float4*)xyzw_dev, n, dst);
+    B2_LAUNCH_CHECK(c);
+    if (dst_on_host) {
+        B2_CUDA_OK(c, cudaMemcpyAsync(out_xyz, dst, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    }
+    return B2_OK;
+}
+
+int b2_project_pixels(b2_handle h, const float* records_host, int n, double fx, double fy, double cx, double cy,
+                      int numpy2_semantics, float* out_xyzw_dev) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!records_host || !out_xyzw_dev))) return set_error(c, B2_ERR_INVALID, "b2_project_pixels: bad arguments");
+    if (n == 0) return B2_OK;
+    B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+    B2_CUDA_OK(c, cudaMemcpyAsync(stage, records_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    project_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, fx, fy, cx, cy, numpy2_semantics,
+                                                                (float4*)out_xyzw_dev);
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
+
+static int voxel_downsample_impl(Context* c, const float* pts_dev, int n, double voxel, const double* origin,
+                                 const double* T, float* out_pts_dev, int* out_keys_dev, int* n_out) {
+    double* T_dev = nullptr;
+    if (T) B2_TRY(upload_T(c, T, 0, &T_dev));
+    DownsampleOut out{(float4*)out_pts_dev, out_keys_dev, nullptr, nullptr};
+    VoxelSortOut vs;
+    B2_TRY(voxel_downsample(c, (const float4*)pts_dev, n, nullptr, nullptr, 1, voxel, origin ? 1 : 0, origin, T_dev,
+                            out, &vs));
+    int* hn = (int*)c->host_mailbox + 700;
+    B2_CUDA_OK(c, cudaMemcpyAsync(hn, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    if (n_out) *n_out = *hn;
+    return B2_OK;
+}
+
+int b2_voxel_downsample(b2_handle h, const float* pts_dev, int n, double voxel, const double* origin,
+                        const double* T, float* out_pts_dev, int* out_keys_dev, int* n_out) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !out_pts_dev))) return set_error(c, B2_ERR_INVALID, "b2_voxel_downsample: bad arguments");
+    if (!(voxel > 0.0)) return set_error(c, B2_ERR_INVALID, "voxel size must be > 0 (got %g)", voxel);
+    B2_TRY(check_T(c, T, "b2_voxel_downsample"));
+    if (n == 0) {
+        if (n_out) *n_out = 0;
+        return B2_OK;
+    }
+    B2_RETRY_WIDE(c, voxel_downsample_impl(c, pts_dev, n, voxel, origin, T, out_pts_dev, out_keys_dev, n_out));
+}
+
+int b2_estimate_normals(b2_handle h, const float* pts_dev, int n, double radius, int max_nn, float* out_normals_dev) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !out_normals_dev))) return set_error(c, B2_ERR_INVALID, "b2_estimate_normals: bad arguments");
+    if (n == 0) return B2_OK;
+    auto body = [&]() -> int {
+        B2_TRY(estimate_normals(c, (const float4*)pts_dev, n, nullptr, radius, max_nn, (float4*)out_normals_dev));
+        return check_status(c);
+    };
+    B2_RETRY_WIDE(c, body());
+}
+
+int b2_nn_search(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt, const double* T,
+                 double radius, int* out_idx_dev, double* out_d2_dev) {
+    CTX(h);
+    if (ns < 0 || nt < 0 || (ns > 0 && (!src_dev || !out_idx_dev)) || (nt > 0 && !tgt_dev))
+        return set_error(c, B2_ERR_INVALID, "b2_nn_search: bad arguments");
+    if (!(radius > 0.0)) return set_error(c, B2_ERR_INVALID, "radius must be > 0");
+    B2_TRY(check_T(c, T, "b2_nn_search"));
+    if (ns == 0) return B2_OK;
+    if (nt == 0) {
+        B2_CUDA_OK(c, cudaMemsetAsync(out_idx_dev, 0xFF, sizeof(int) * (size_t)ns, c->stream));
+        if (out_d2_dev) B2_CUDA_OK(c, cudaMemsetAsync(out_d2_dev, 0, sizeof(double) * (size_t)ns, c->stream));
+        return B2_OK;
+    }
+    auto body = [&]() -> int {
+        double* T_dev = nullptr;
+        if (T) B2_TRY(upload_T(c, T, 1, &T_dev));
+        GridView g;
+        B2_TRY(grid_build(c, (const float4*)tgt_dev, nt, nullptr, nullptr, 1, radius, WS_GRID_ENTRIES, &g));
+        IcpParams prm{radius, 0, 0.0, 0.0, 0};
+        B2_WS(c, res, IcpResultDev, WS_BATCH_D, sizeof(IcpResultDev));
+        B2_TRY(icp_run(c, (const float4*)src_dev, ns, nullptr, nullptr, 1, g, nullptr, nullptr, T_dev, prm, res,
+                       out_idx_dev, out_d2_dev, /*search_only=*/1, 0));
+        return check_status(c);
+    };
+    B2_RETRY_WIDE(c, body());
+}
+
+int b2_icp(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt, const float* tgt_normals_dev,
+           const double* init, const b2_icp_params* params, b2_icp_result* out, int* out_corr_dev) {
+    CTX(h);
+    B2_TRY(check_params(c, params));
+    if (ns <= 0 || nt <= 0 || !src_dev || !tgt_dev || !out) return set_error(c, B2_ERR_INVALID, "b2_icp: empty cloud or NULL argument");
+    if (params->mode == B2_ICP_POINT_TO_PLANE && !tgt_normals_dev)
+        return set_error(c, B2_ERR_INVALID, "point-to-plane ICP requires target normals");
+    B2_TRY(check_T(c, init, "b2_icp"));
+    auto body = [&]() -> int {
+        double* init_dev = nullptr;
+        if (init) B2_TRY(upload_T(c, init, 2, &init_dev));
+        GridView g;
+        B2_TRY(grid_build(c, (const float4*)tgt_dev, nt, nullptr, nullptr, 1, params->max_correspondence_distance,
+                          WS_GRID_ENTRIES, &g));
+        B2_WS(c, res, IcpResultDev, WS_BATCH_D, sizeof(IcpResultDev));
+        B2_TRY(icp_run(c, (const float4*)src_dev, ns, nullptr, nullptr, 1, g, (const float4*)tgt_normals_dev, nullptr,
+                       init_dev, to_internal(params), res, out_corr_dev, nullptr, 0, /*check_every=*/16));
+        IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
+        B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+        B2_TRY(check_status(c));
+        fill_result(hr, out);
+        return B2_OK;
+    };
+    B2_RETRY_WIDE(c, body());
+}
+
+int b2_transform(b2_handle h, const float* pts_dev, int n, const double* T, float* out_pts_dev) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !out_pts_dev)) || !T) return set_error(c, B2_ERR_INVALID, "b2_transform: bad arguments");
+    B2_TRY(check_T(c, T, "b2_transform"));
+    if (n == 0) return B2_OK;
+    double* T_dev = nullptr;
+    B2_TRY(upload_T(c, T, 3, &T_dev));
+    transform_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>((const float4*)pts_dev, n, T_dev, (float4*)out_pts_dev);
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
+
+int b2_map_init(b2_handle h, double voxel, const double* origin, double max_corr, long long capacity_cells) {
+    CTX(h);
+    return map_init(c, voxel, origin, max_corr, capacity_cells);
+}
+
+int b2_map_reset(b2_handle h) {
+    CTX(h);
+    return map_reset(c);
+}
+
+int b2_map_fuse(b2_handle h, const float* pts_dev, int n, const double* T) {
+    CTX(h);
+    if (n < 0 || (n > 0 && !pts_dev)) return set_error(c, B2_ERR_INVALID, "b2_map_fuse: bad arguments");
+    B2_TRY(check_T(c, T, "b2_map_fuse"));
+    if (n == 0) return B2_OK;
+    auto body = [&]() -> int {
+        double* T_dev = nullptr;
+        if (T) B2_TRY(upload_T(c, T, 4, &T_dev));
+        B2_TRY(map_fuse(c, (const float4*)pts_dev, n, nullptr, T_dev));
+        return check_status(c);
+    };
+    // a KEY_RANGE failure happens before the merge kernel touches the map, so the retry is safe
+    B2_RETRY_WIDE(c, body());
+}
+
+int b2_map_size(b2_handle h, long long* n_voxels) {
+    CTX(h);
+    return map_counts(c, nullptr, n_voxels);
+}
+
+int b2_map_export(b2_handle h, float* out_pts_dev, int* out_keys_dev, long long max_out, long long* n_out) {
+    CTX(h);
+    if (!out_pts_dev || max_out < 0) return set_error(c, B2_ERR_INVALID, "b2_map_export: bad arguments");
+    return map_export(c, (float4*)out_pts_dev, out_keys_dev, max_out, n_out);
+}
+
+int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
+               b2_icp_result* out) {
+    CTX(h);
+    B2_TRY(check_params(c, params));
+    if (ns <= 0 || !src_dev || !out) return set_error(c, B2_ERR_INVALID, "b2_map_icp: empty cloud or NULL argument");
+    if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "the resident map holds no normals: point-to-point only");
+    B2_TRY(check_T(c, init, "b2_map_icp"));
+    GridView g;
+    B2_TRY(map_grid_view(c, &g));
+    if (params->max_correspondence_distance > map_max_corr(c) * (1.0 + 1e-12))
+        return set_error(c, B2_ERR_INVALID, "max_correspondence_distance %g exceeds the map's cell edge %g",
+                         params->max_correspondence_distance, map_max_corr(c));
+    double* init_dev = nullptr;
+    if (init) B2_TRY(upload_T(c, init, 5, &init_dev));
+    IcpResultDev* res = map_result_dev(c);
+    B2_TRY(icp_run(c, (const float4*)src_dev, ns, nullptr, nullptr, 1, g, nullptr, nullptr, init_dev,
+                   to_internal(params), res, nullptr, nullptr, 0, 16));
+    IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
+    B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    fill_result(hr, out);
+    return B2_OK;
+}
+
+int b2_slam_set_pose(b2_handle h, const double* T) {
+    CTX(h);
+    if (!T) return set_error(c, B2_ERR_INVALID, "b2_slam_set_pose: NULL transform");
+    B2_TRY(check_T(c, T, "b2_slam_set_pose"));
+    double* pose = map_pose_dev(c);
+    if (!pose) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
+    B2_CUDA_OK(c, cudaMemcpyAsync(pose, T, sizeof(double) * 16, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2_slam_get_pose(b2_handle h, double* T) {
+    CTX(h);
+    double* pose = map_pose_dev(c);
+    if (!pose || !T) return set_error(c, B2_ERR_STATE, "map not initialised or NULL output");
+    B2_CUDA_OK(c, cudaMemcpyAsync(T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+static int slam_scan_impl(Context* c, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
+                          b2_icp_result* out, bool map_empty) {
+    B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+    B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)n);
+    B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);
+    B2_LAUNCH_CHECK(c);
+    double* pose = map_pose_dev(c);
+    IcpResultDev* res = map_result_dev(c);
+    if (!map_empty) {
+        const float4* src = scan;
+        const int* ns_dev = nullptr;
+        if (ds_voxel > 0.0) {
+            B2_WS(c, sdown, float4, WS_SRC_DOWN, sizeof(float4) * (size_t)n);
+            DownsampleOut dso{sdown, nullptr, nullptr, nullptr};
+            VoxelSortOut vs;
+            B2_TRY(voxel_downsample(c, scan, n, nullptr, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
+            // keep the voxel count where later sorts cannot overwrite it
+            B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
+            B2_CUDA_OK(c, cudaMemcpyAsync(cnt, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            src = sdown;
+            ns_dev = cnt;
+        }
+        GridView g;
+        B2_TRY(map_grid_view(c, &g));
+        B2_TRY(icp_run(c, src, n, nullptr, ns_dev, 1, g, nullptr, nullptr, pose, to_internal(params), res, nullptr,
+                       nullptr, 0, 0));
+        copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose);
+        B2_LAUNCH_CHECK(c);
+    }
+    B2_TRY(map_fuse(c, scan, n, nullptr, pose));
+    if (out) {
+        IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
+        if (map_empty) {
+            B2_CUDA_OK(c, cudaMemcpyAsync(hr->T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
+            hr->fitness = 0.0; hr->rmse = 0.0; hr->iterations = 0; hr->n_corr = 0;
+        } else {
+            B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+        }
+        B2_TRY(check_status(c));
+        fill_result(hr, out);
+    }
+    return B2_OK;
+}
+
+int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
+                 b2_icp_result* out) {
+    CTX(h);
+    B2_TRY(check_params(c, params));
+    if (n <= 0 || !xyz_host) return set_error(c, B2_ERR_INVALID, "b2_slam_scan: empty scan");
+    if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "the resident map holds no normals: point-to-point only");
+    GridView g;
+    B2_TRY(map_grid_view(c, &g));
+    if (params->max_correspondence_distance > map_max_corr(c) * (1.0 + 1e-12))
+        return set_error(c, B2_ERR_INVALID, "max_correspondence_distance %g exceeds the map's cell edge %g",
+                         params->max_correspondence_distance, map_max_corr(c));
+    // "first scan becomes the map" (icp_processor.py:53-56): decided on the host from the fuse history
+    const bool map_empty = map_is_empty_host(c);
+    return slam_scan_impl(c, xyz_host, n, ds_voxel, params, out, map_empty);
+}
+
+int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total, const float* tgt_dev,
+                 const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel, const double* init_dev,
+                 const b2_icp_params* params, b2_icp_result* results_dev) {
+    CTX(h);
+    B2_TRY(check_params(c, params));
+    if (n_pairs <= 0 || src_total <= 0 || tgt_total <= 0 || !src_dev || !tgt_dev || !src_offsets_dev ||
+        !tgt_offsets_dev || !results_dev)
+        return set_error(c, B2_ERR_INVALID, "b2_icp_batch: empty batch or NULL argument");
+    if (n_pairs > 32768) return set_error(c, B2_ERR_INVALID, "b2_icp_batch: at most 32768 pairs per call (got %d)", n_pairs);
+    if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "b2_icp_batch: point-to-point only");
+    HintGuard guard(c, 8);
+    const float4* src = (const float4*)src_dev;
+    const float4* tgt = (const float4*)tgt_dev;
+    const int* soffs = src_offsets_dev;
+    const int* toffs = tgt_offsets_dev;
+    if (ds_voxel > 0.0) {
+        B2_WS(c, sd, float4, WS_BATCH_A, sizeof(float4) * (size_t)src_total);
+        B2_WS(c, so, int, WS_OFFS_A, sizeof(int) * ((size_t)n_pairs + 1));
+        DownsampleOut o1{sd, nullptr, nullptr, so};
+        B2_TRY(voxel_downsample(c, src, src_total, nullptr, src_offsets_dev, n_pairs, ds_voxel, 0, nullptr, nullptr, o1, nullptr));
+        B2_WS(c, td, float4, WS_BATCH_B, sizeof(float4) * (size_t)tgt_total);
+        B2_WS(c, to, int, WS_OFFS_B, sizeof(int) * ((size_t)n_pairs + 1));
+        DownsampleOut o2{td, nullptr, nullptr, to};
+        B2_TRY(voxel_downsample(c, tgt, tgt_total, nullptr, tgt_offsets_dev, n_pairs, ds_voxel, 0, nullptr, nullptr, o2, nullptr));
+        src = sd; tgt = td; soffs = so; toffs = to;
+    }
+    GridView g;
+    B2_TRY(grid_build(c, tgt, tgt_total, nullptr, toffs, n_pairs, params->max_correspondence_distance, WS_GRID_ENTRIES, &g));
+    B2_TRY(icp_run(c, src, src_total, soffs, nullptr, n_pairs, g, nullptr, toffs, init_dev, to_internal(params),
+                   (IcpResultDev*)results_dev, nullptr, nullptr, 0, 0));
+    return B2_OK;
+}
+
+}  // extern "C"

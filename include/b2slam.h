@@ -1,0 +1,158 @@
+/* b2slam.h — C ABI of libb2slam.so, the B200 (sm_100a) scan-registration and
+ * map-fusion hot path.
+ *
+ * The reference (MatthewKazan/3D-lidar-slam) has no FFI of its own: its plugin
+ * `ICPProcessor` (src/slam/scripts/point_cloud_processors/icp_processor.py:18-160)
+ * reaches its arithmetic through Open3D's pybind11 module.  Each entry point
+ * below is what a binding for that path binds instead; the Open3D call and the
+ * reference line it replaces are cited per function.  Plain pointers and sizes
+ * only — no torch / numpy types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns B2_OK (0) or a negative B2_ERR_* code;
+ *     b2_last_error(h) returns the message of the last failure on that handle.
+ *   - `*_dev` pointers are caller-owned CUDA device pointers on the handle's
+ *     device.  Point clouds are float32 [n,4] rows (x, y, z, w): 16-byte rows so
+ *     one point is one 128-bit load; w is ignored on input unless stated.
+ *   - 4x4 transforms are row-major float64[16] in HOST memory, last row must be
+ *     (0,0,0,1).
+ *   - all work is enqueued on the handle's stream (b2_set_stream); functions
+ *     that return data-dependent scalars to the host synchronise that stream.
+ *   - there is no CPU fallback anywhere: without a CUDA device b2_create fails.
+ */
+#ifndef B2SLAM_H_
+#define B2SLAM_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2_context_s* b2_handle;
+
+enum {
+    B2_OK = 0,
+    B2_ERR_INVALID = -1,   /* bad argument */
+    B2_ERR_CUDA = -2,      /* CUDA runtime failure (message has the call) */
+    B2_ERR_CAPACITY = -3,  /* resident map / hash table full */
+    B2_ERR_KEY_RANGE = -4, /* voxel index outside int32 / packed key range */
+    B2_ERR_STATE = -5      /* call order violated (e.g. map not initialised) */
+};
+
+enum { B2_ICP_POINT_TO_POINT = 0, B2_ICP_POINT_TO_PLANE = 1 };
+
+/* o3d.pipelines.registration.ICPConvergenceCriteria + max_correspondence_distance
+ * + estimation method (icp_processor.py:103-113). */
+typedef struct b2_icp_params {
+    double max_correspondence_distance;
+    int max_iteration;
+    int mode; /* B2_ICP_POINT_TO_POINT | B2_ICP_POINT_TO_PLANE */
+    double relative_fitness;
+    double relative_rmse;
+} b2_icp_params;
+
+/* o3d RegistrationResult: transformation, fitness, inlier_rmse (+ iterations run). */
+typedef struct b2_icp_result {
+    double transformation[16];
+    double fitness;
+    double inlier_rmse;
+    int iterations;
+    int n_correspondences;
+} b2_icp_result;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+const char* b2_version(void);
+int b2_create(int device, b2_handle* out);
+int b2_destroy(b2_handle h);
+const char* b2_last_error(b2_handle h);
+int b2_set_stream(b2_handle h, void* cuda_stream); /* cudaStream_t; NULL = handle-owned stream */
+int b2_synchronize(b2_handle h);
+/* number of kernels this handle has launched so far (bench.py "gpu_launches") */
+unsigned long long b2_launch_count(b2_handle h);
+
+/* ---- layout helpers ----------------------------------------------------- */
+/* float32 [n,3] (host when src_on_host != 0, else device) -> float32 [n,4] device rows.
+ * Replaces o3d.utility.Vector3dVector(points) (icp_processor.py:60,65). */
+int b2_pack_xyz(b2_handle h, const float* xyz, int n, int src_on_host, float* out_xyzw_dev);
+/* float32 [n,4] device rows -> float32 [n,3] (host or device).  Replaces
+ * np.asarray(pcd.points) (icp_processor.py:74). */
+int b2_unpack_xyz(b2_handle h, const float* xyzw_dev, int n, float* out_xyz, int dst_on_host);
+/* ProcessPointClouds.project_pixel_to_3d (generic_point_cloud_processor.py:93-108):
+ * records (x_px, y_px, depth_m) float32 [n,3] on the host -> metric float32 [n,4] device rows.
+ * numpy2_semantics != 0: float32 arithmetic (NEP 50); else float64 arithmetic rounded once. */
+int b2_project_pixels(b2_handle h, const float* records_host, int n, double fx, double fy, double cx, double cy,
+                      int numpy2_semantics, float* out_xyzw_dev);
+
+/* ---- stateless primitives ----------------------------------------------- */
+/* PointCloud.voxel_down_sample(voxel) (icp_processor.py:90-91,132-133).
+ * origin == NULL: Open3D's own origin (min_bound - voxel/2).  T != NULL: points are
+ * transformed first (fuses icp_processor.py:73).  Output order is canonical
+ * (lexicographic voxel key); out_pts_dev [n,4] (w = bit pattern of the int32 point
+ * count of the voxel), out_keys_dev int32 [n,3] or NULL, *n_out = voxel count. */
+int b2_voxel_downsample(b2_handle h, const float* pts_dev, int n, double voxel, const double* origin,
+                        const double* T, float* out_pts_dev, int* out_keys_dev, int* n_out);
+
+/* PointCloud.estimate_normals(KDTreeSearchParamHybrid(radius, max_nn))
+ * (icp_processor.py:94-99).  out_normals_dev float32 [n,4] (w = 0).
+ * Normal sign is unspecified (no orientation step), as in Open3D. */
+int b2_estimate_normals(b2_handle h, const float* pts_dev, int n, double radius, int max_nn,
+                        float* out_normals_dev);
+
+/* One correspondence pass: KDTreeFlann.SearchHybrid(T*p, radius, 1) per source point
+ * (the Eval step of registration_icp).  out_idx_dev int32 [ns]
+ * (-1 = no neighbour with d^2 < radius^2), out_d2_dev float64 [ns] or NULL. */
+int b2_nn_search(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt, const double* T,
+                 double radius, int* out_idx_dev, double* out_d2_dev);
+
+/* o3d.pipelines.registration.registration_icp(source, target, max_corr, init, estimation,
+ * criteria) (icp_processor.py:103-113).  tgt_normals_dev is required for
+ * point-to-plane.  out_corr_dev int32 [ns] or NULL receives the final correspondence map. */
+int b2_icp(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt,
+           const float* tgt_normals_dev, const double* init, const b2_icp_params* params,
+           b2_icp_result* out, int* out_corr_dev);
+
+/* PointCloud.transform(T) (icp_processor.py:73). In-place allowed. */
+int b2_transform(b2_handle h, const float* pts_dev, int n, const double* T, float* out_pts_dev);
+
+/* ---- resident global map ------------------------------------------------ */
+/* The reference keeps the map as a host ndarray that it re-voxelises, re-indexes and
+ * re-uploads for every scan (icp_processor.py:64-65,91,103).  Here the map is a
+ * GPU-resident voxel hash: (sum xyz, n) per voxel of edge `voxel` anchored at
+ * `origin`, grouped in cells of edge >= max_corr so it doubles as the uniform grid
+ * of the correspondence search.  capacity_cells: hash slots (power of two is
+ * enforced by rounding up); the map reports B2_ERR_CAPACITY beyond 70% load. */
+int b2_map_init(b2_handle h, double voxel, const double* origin, double max_corr, long long capacity_cells);
+int b2_map_reset(b2_handle h); /* ProcessPointClouds.reset (generic_point_cloud_processor.py:128-138) */
+/* point_cloud.transform(T) + (point_cloud + map) + voxel merge (icp_processor.py:73-74,132-133). */
+int b2_map_fuse(b2_handle h, const float* pts_dev, int n, const double* T);
+int b2_map_size(b2_handle h, long long* n_voxels);
+/* Voxel centroids in canonical key order: out_pts_dev float32 [max_out,4] (w = count bits),
+ * out_keys_dev int32 [max_out,3] or NULL. */
+int b2_map_export(b2_handle h, float* out_pts_dev, int* out_keys_dev, long long max_out, long long* n_out);
+/* registration_icp with the resident map as the target (icp_processor.py:68-69,103-113). */
+int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
+               b2_icp_result* out);
+
+/* ---- fused per-scan step (ICPProcessor.construct_global_map, icp_processor.py:43-75) ---- */
+/* xyz_host: float32 [n,3] scan in the sensor frame (the plugin-boundary format).
+ * Runs: upload -> voxel_down_sample(ds_voxel) -> ICP against the resident map seeded with
+ * the previous pose (kept on the device) -> transform + fuse the RAW scan.  When the map
+ * is empty the scan is fused with the current pose and no ICP runs (icp_processor.py:53-56).
+ * out may be NULL (no host read-back, fully asynchronous). */
+int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
+                 b2_icp_result* out);
+int b2_slam_set_pose(b2_handle h, const double* T);
+int b2_slam_get_pose(b2_handle h, double* T);
+
+/* ---- batched independent pairs (loop-closure candidates / offline replay) ---- */
+/* src_dev/tgt_dev: concatenated float32 [sum,4]; *_offsets_dev: int32 [n_pairs+1] (device).
+ * ds_voxel > 0: both clouds of every pair are voxel-down-sampled first (icp_processor.py:90-91).
+ * init_dev: float64 [n_pairs,16] device or NULL (identity).  results_dev: device array of
+ * n_pairs b2_icp_result records (gathered across ranks by the caller, e.g. with NCCL). */
+int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total,
+                 const float* tgt_dev, const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel,
+                 const double* init_dev, const b2_icp_params* params, b2_icp_result* results_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2SLAM_H_ */
