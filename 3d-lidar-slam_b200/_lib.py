@@ -23,7 +23,7 @@ EXPORTS = [
     "b2_launch_count", "b2_pack_xyz", "b2_unpack_xyz", "b2_project_pixels", "b2_voxel_downsample",
     "b2_estimate_normals", "b2_nn_search", "b2_icp", "b2_transform", "b2_map_init", "b2_map_reset",
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
-    "b2_slam_get_pose", "b2_icp_batch",
+    "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
 ]
 
 
@@ -84,6 +84,8 @@ def load():
         "b2_map_export": [vp, vp, vp, i64, C.POINTER(i64)],
         "b2_map_icp": [vp, vp, i32, pd, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
+        "b2_slam_scan_dev": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
+        "b2_map_stencil_candidates": [vp, vp, i32, pd, C.POINTER(i64)],
         "b2_slam_set_pose": [vp, pd],
         "b2_slam_get_pose": [vp, pd],
         "b2_icp_batch": [vp, vp, vp, i32, vp, vp, i32, i32, f64, vp, C.POINTER(IcpParams), vp],
@@ -306,6 +308,22 @@ class Engine:
         self._check(self.lib.b2_slam_scan(self.h, xyz_host.ctypes.data, xyz_host.shape[0], float(ds_voxel),
                                           C.byref(params), C.byref(res) if want_result else None))
         return res
+
+    def slam_scan_dev(self, scan4, ds_voxel: float, params: IcpParams, want_result: bool = False):
+        """Same step for a scan already resident on the device (float32 [n,4]); asynchronous unless
+        a result is requested."""
+        scan4 = self._pts(scan4)
+        res = IcpResult() if want_result else None
+        self._check(self.lib.b2_slam_scan_dev(self.h, scan4.data_ptr(), scan4.shape[0], float(ds_voxel),
+                                              C.byref(params), C.byref(res) if want_result else None))
+        return res
+
+    def stencil_candidates(self, src, T=None) -> int:
+        src = self._pts(src)
+        _t, tp = _dptr(T)
+        n = C.c_longlong(0)
+        self._check(self.lib.b2_map_stencil_candidates(self.h, src.data_ptr(), src.shape[0], tp, C.byref(n)))
+        return int(n.value)
 
     def set_pose(self, T):
         _t, tp = _dptr(T)

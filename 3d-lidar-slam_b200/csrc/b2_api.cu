@@ -487,13 +487,17 @@ int b2_slam_get_pose(b2_handle h, double* T) {
     return B2_OK;
 }
 
-static int slam_scan_impl(Context* c, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
-                          b2_icp_result* out, bool map_empty) {
-    B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
-    B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)n);
-    B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);
-    B2_LAUNCH_CHECK(c);
+static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
+                          const b2_icp_params* params, b2_icp_result* out, bool map_empty) {
+    const float4* scan = scan_dev;
+    if (!scan) {
+        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+        B2_WS(c, packed, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)n);
+        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, packed);
+        B2_LAUNCH_CHECK(c);
+        scan = packed;
+    }
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
     if (!map_empty) {
@@ -532,11 +536,10 @@ static int slam_scan_impl(Context* c, const float* xyz_host, int n, double ds_vo
     return B2_OK;
 }
 
-int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
-                 b2_icp_result* out) {
-    CTX(h);
+static int slam_scan_entry(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
+                           const b2_icp_params* params, b2_icp_result* out) {
     B2_TRY(check_params(c, params));
-    if (n <= 0 || !xyz_host) return set_error(c, B2_ERR_INVALID, "b2_slam_scan: empty scan");
+    if (n <= 0 || (!xyz_host && !scan_dev)) return set_error(c, B2_ERR_INVALID, "b2_slam_scan: empty scan");
     if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "the resident map holds no normals: point-to-point only");
     GridView g;
     B2_TRY(map_grid_view(c, &g));
@@ -545,7 +548,37 @@ int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, con
                          params->max_correspondence_distance, map_max_corr(c));
     // "first scan becomes the map" (icp_processor.py:53-56): decided on the host from the fuse history
     const bool map_empty = map_is_empty_host(c);
-    return slam_scan_impl(c, xyz_host, n, ds_voxel, params, out, map_empty);
+    return slam_scan_impl(c, xyz_host, scan_dev, n, ds_voxel, params, out, map_empty);
+}
+
+int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
+                 b2_icp_result* out) {
+    CTX(h);
+    return slam_scan_entry(c, xyz_host, nullptr, n, ds_voxel, params, out);
+}
+
+int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_voxel, const b2_icp_params* params,
+                     b2_icp_result* out) {
+    CTX(h);
+    return slam_scan_entry(c, nullptr, (const float4*)scan_xyzw_dev, n, ds_voxel, params, out);
+}
+
+int b2_map_stencil_candidates(b2_handle h, const float* src_dev, int ns, const double* T, long long* n_candidates) {
+    CTX(h);
+    if (ns <= 0 || !src_dev || !n_candidates) return set_error(c, B2_ERR_INVALID, "b2_map_stencil_candidates: bad arguments");
+    B2_TRY(check_T(c, T, "b2_map_stencil_candidates"));
+    GridView g;
+    B2_TRY(map_grid_view(c, &g));
+    double* T_dev = nullptr;
+    if (T) B2_TRY(upload_T(c, T, 6, &T_dev));
+    B2_WS(c, cnt, unsigned long long, WS_COUNTS, sizeof(unsigned long long) * 2);
+    B2_CUDA_OK(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 2, c->stream));
+    B2_TRY(map_stencil_count(c, (const float4*)src_dev, ns, T_dev, g, cnt));
+    unsigned long long* hc = (unsigned long long*)((char*)c->host_mailbox + 2048);
+    B2_CUDA_OK(c, cudaMemcpyAsync(hc, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    *n_candidates = (long long)*hc;
+    return B2_OK;
 }
 
 int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total, const float* tgt_dev,

@@ -300,6 +300,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
             const IcpParams& prm, IcpResultDev* results_dev, int* corr_out, double* d2_out, int search_only,
             int check_every);
 
+int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev, const GridView& g,
+                      unsigned long long* total_dev);
+
 // b2_normals.cu
 int estimate_normals(Context* c, const float4* pts, int n_max, const int* n_dev, double radius, int max_nn,
                      float4* normals_out);

@@ -505,7 +505,46 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                                                                    tickets, res, corr, ndone, d2_out, search_only);
 }
 
+// Candidate census of the resident-map stencil (the data-dependent term of the byte model).
+__global__ void __launch_bounds__(256)
+stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __restrict__ T,
+                     const CellEntry* __restrict__ entries, unsigned mask, const GridMeta* __restrict__ meta,
+                     unsigned long long* __restrict__ total) {
+    const int lane = threadIdx.x & 31;
+    const int q = (blockIdx.x * 256 + threadIdx.x) >> 5;
+    if (q >= ns) return;
+    const float4 p = __ldg(src + q);
+    D3 P{(double)p.x, (double)p.y, (double)p.z};
+    if (T) P = xform_strict(T, P.x, P.y, P.z);
+    const int brick = meta->brick;
+    int cx = voxel_coord(P.x, meta->origin[0], meta->cell);
+    int cy = voxel_coord(P.y, meta->origin[1], meta->cell);
+    int cz = voxel_coord(P.z, meta->origin[2], meta->cell);
+    if (brick > 1) {
+        cx = floor_div(cx, brick);
+        cy = floor_div(cy, brick);
+        cz = floor_div(cz, brick);
+    }
+    unsigned cnt = 0;
+    if (lane < 27) {
+        const int nx = cx + lane / 9 - 1, ny = cy + (lane / 3) % 3 - 1, nz = cz + lane % 3 - 1;
+        const unsigned long long key = map_cell_key(nx, ny, nz);
+        const CellEntry e = grid_lookup(entries, mask, key);
+        if (e.key == key) cnt = e.cnt;
+    }
+    cnt = __reduce_add_sync(kFull, cnt);
+    if (lane == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+}
+
 }  // namespace
+
+int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev, const GridView& g,
+                      unsigned long long* total_dev) {
+    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.mask,
+                                                                                  g.meta, total_dev);
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
 
 int icp_grid_x(int ns_max, int n_pairs) {
     // one CTA of 16 warps per ~64 queries, capped at two resident CTAs per SM for a

@@ -1,0 +1,167 @@
+"""B200ICPProcessor — drop-in replacement for the reference's ``ICPProcessor``
+(src/slam/scripts/point_cloud_processors/icp_processor.py:18-160).
+
+Same constructor, same ``construct_global_map`` / ``downsample_global_map`` /
+``process`` / ``reset`` contract, same hard-coded defaults (voxel 0.02 m, max
+correspondence 2.5 voxels, point-to-point, 500 iterations, 1e-6 / 1e-6), but every
+Open3D call is replaced by a call into libb2slam.so (hand-written sm_100a kernels).
+There is no CPU fallback: constructing the processor without a CUDA device raises.
+
+Two map modes:
+
+``mode="resident"`` (default, the fast path)
+    The global map is a GPU-resident voxel hash (b2_map.cu).  Per scan one C-ABI
+    call (``b2_slam_scan``) uploads the scan, voxel-down-samples it, runs ICP against
+    the resident map seeded with the previous pose and fuses the raw scan — O(scan)
+    work, nothing O(map), no host round trip inside the ICP loop.  The map is
+    anchored at a fixed voxel origin (the reference re-anchors at the growing map's
+    min bound every scan, icp_processor.py:91) and ``global_map`` is the voxel
+    centroids at ``map_voxel`` resolution, materialised on the host lazily.
+
+``mode="reference"``
+    The reference's exact sequence (icp_processor.py:43-75,77-119) on GPU
+    primitives: the raw map is kept point-for-point (on the device), both clouds
+    are re-voxelised per scan with Open3D's per-cloud origin, the raw scan is
+    transformed and PREPENDED.  Used by the parity tests against the CPU oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib
+from .generic_point_cloud_processor import ProcessPointClouds
+from .logging_shim import get_logger
+
+
+class B200ICPProcessor(ProcessPointClouds):
+    def __init__(self, config_path: str, reset_event, data_transfer, *, mode: str = "resident",
+                 voxel_size: float = 0.02, max_correspondence_distance: float | None = None,
+                 max_iteration: int = 500, relative_fitness: float = 1e-6, relative_rmse: float = 1e-6,
+                 map_voxel: float | None = None, map_origin=(0.0, 0.0, 0.0), map_capacity_cells: int = 1 << 22,
+                 maintenance: str = "voxel", numpy2_projection: bool | None = None, device: int = 0,
+                 logger=None):
+        if mode not in ("resident", "reference"):
+            raise ValueError(f"unknown mode {mode!r}")
+        if maintenance not in ("voxel", "off", "full"):
+            raise ValueError(f"unknown maintenance {maintenance!r}")
+        self._map_cache = None
+        self._mode = mode
+        self._engine = _lib.Engine(device)  # raises without CUDA / without the built library
+        self._voxel = float(voxel_size)
+        self._max_corr = float(max_correspondence_distance) if max_correspondence_distance else 2.5 * self._voxel
+        self._params = _lib.make_params(self._max_corr, max_iteration, _lib.P2P, relative_fitness, relative_rmse)
+        self._map_voxel = float(map_voxel) if map_voxel else self._voxel
+        self._map_origin = np.asarray(map_origin, dtype=np.float64)
+        self._map_capacity = int(map_capacity_cells)
+        self._maintenance = maintenance
+        self._numpy2 = (int(np.__version__.split(".")[0]) >= 2) if numpy2_projection is None else bool(numpy2_projection)
+        self._raw_map = None       # reference mode: CUDA float32 [N,4], newest scan first
+        self._resident_ready = False
+        self.last_result = None    # b2_icp_result of the most recent registration
+        super().__init__(config_path, reset_event, data_transfer,
+                         logger if logger is not None else get_logger("b200 icp processor"))
+
+    # -- global_map: lazy device -> host materialisation ----------------------
+    @property
+    def global_map(self):
+        if self._map_cache is None:
+            if self._mode == "resident" and self._resident_ready and self.point_clouds_in_map > 0:
+                pts, _ = self._engine.map_export(want_keys=False)
+                self._map_cache = self._engine.unpack(pts) if pts.shape[0] else np.zeros((0, 3), np.float32)
+            elif self._mode == "reference" and self._raw_map is not None:
+                self._map_cache = self._engine.unpack(self._raw_map)
+        return self._map_cache
+
+    @global_map.setter
+    def global_map(self, value):
+        self._map_cache = value
+
+    # -- per-scan entry points -----------------------------------------------
+    def project_pixel_to_3d(self, points) -> np.ndarray:
+        """Vectorised statement of generic_point_cloud_processor.py:93-108 (float32 [N,3])."""
+        rec = _records_to_array(points)
+        if self._numpy2:
+            r = rec.astype(np.float32)
+            x = (r[:, 0] - np.float32(self.cx)) * r[:, 2] / np.float32(self.fx)
+            y = (r[:, 1] - np.float32(self.cy)) * r[:, 2] / np.float32(self.fy)
+            return np.stack([x, y, r[:, 2]], axis=1)
+        r = rec.astype(np.float64)
+        x = (r[:, 0] - self.cx) * r[:, 2] / self.fx
+        y = (r[:, 1] - self.cy) * r[:, 2] / self.fy
+        return np.stack([x, y, r[:, 2]], axis=1).astype(np.float32)
+
+    def construct_global_map(self, points: np.ndarray) -> None:
+        """ICPProcessor.construct_global_map (icp_processor.py:43-75)."""
+        pts = np.ascontiguousarray(points, dtype=np.float32)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise ValueError(f"expected [N,3] points, got {pts.shape}")
+        self._map_cache = None
+        if self._mode == "resident":
+            self._construct_resident(pts)
+        else:
+            self._construct_reference(self._engine.pack(pts))
+
+    def downsample_global_map(self) -> np.ndarray:
+        """ICPProcessor.downsample_global_map (icp_processor.py:150-160) returns the map as is."""
+        return self.global_map
+
+    def reset(self) -> None:
+        if self._resident_ready:
+            self._engine.map_reset()
+        self._raw_map = None
+        self._map_cache = None
+        self.last_result = None
+        super().reset()
+
+    # -- resident mode --------------------------------------------------------
+    def _construct_resident(self, pts: np.ndarray) -> None:
+        eng = self._engine
+        if not self._resident_ready:
+            eng.map_init(self._map_voxel, self._map_origin, self._max_corr, self._map_capacity)
+            self._resident_ready = True
+        first = self.point_clouds_in_map == 0
+        res = eng.slam_scan(pts, self._voxel, self._params)
+        if first:
+            self.point_clouds_in_map += 1  # icp_processor.py:54 (the caller increments once more)
+            return
+        self.last_result = res
+        self.previous_transformation.append(res.matrix())
+
+    # -- reference mode -------------------------------------------------------
+    def _construct_reference(self, scan4) -> None:
+        eng = self._engine
+        torch = eng.torch
+        if self.point_clouds_in_map == 0:
+            self.point_clouds_in_map += 1
+            self._raw_map = scan4
+            return
+        source_down, _ = eng.voxel_downsample(scan4, self._voxel, want_keys=False)
+        target_down, _ = eng.voxel_downsample(self._raw_map, self._voxel, want_keys=False)
+        # icp_processor.py:94-99 estimates normals on both clouds here and never uses them
+        # (point-to-point estimation): skipped, the result does not depend on them.
+        res, _ = eng.icp(source_down, target_down, self._params, init=self.previous_transformation[-1])
+        self.last_result = res
+        T = res.matrix()
+        self.previous_transformation.append(T)
+        moved = eng.transform(scan4, T)
+        with torch.cuda.stream(eng.stream):
+            self._raw_map = torch.cat([moved, self._raw_map], dim=0)
+        self._do_stuff()
+
+    def _do_stuff(self) -> None:
+        """ICPProcessor.do_stuff (icp_processor.py:121-148): periodic 1 mm re-voxelisation (+ outlier
+        filters, which are rows f2 of the scope table and not built yet)."""
+        if self._maintenance == "off" or self.point_clouds_in_map < 10:
+            return
+        if self.point_clouds_in_map % 10 == 0 or self.data_transfer.pixel_depth_map_queue.empty():
+            if self._maintenance == "full":
+                raise NotImplementedError("statistical / radius outlier removal on the GPU is not built yet")
+            self._raw_map, _ = self._engine.voxel_downsample(self._raw_map, 0.001, want_keys=False)
+            self._raw_map = self._raw_map.contiguous()
+
+
+def _records_to_array(points) -> np.ndarray:
+    a = np.asarray(points)
+    if a.dtype.names:  # structured array from sensor_msgs_py.point_cloud2.read_points (input_handler.py:65)
+        a = np.stack([a[n] for n in a.dtype.names[:3]], axis=1)
+    return np.asarray(a).reshape(-1, 3)

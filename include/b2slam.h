@@ -140,6 +140,13 @@ int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, co
  * out may be NULL (no host read-back, fully asynchronous). */
 int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
                  b2_icp_result* out);
+/* Same step for a scan that already lives on the device as float32 [n,4] rows (offline replay of
+ * device-resident batches): no upload, otherwise identical. */
+int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_voxel, const b2_icp_params* params,
+                     b2_icp_result* out);
+/* Number of resident-map points inside the 27-cell stencils of the transformed source points —
+ * the data-dependent term of the search's algorithmic-byte model. */
+int b2_map_stencil_candidates(b2_handle h, const float* src_dev, int ns, const double* T, long long* n_candidates);
 int b2_slam_set_pose(b2_handle h, const double* T);
 int b2_slam_get_pose(b2_handle h, double* T);
 

@@ -425,28 +425,6 @@ bool ldlt6_solve(const double A_in[36], const double b[6], double x[6]) {
     return true;
 }
 
-double det6(const double A_in[36]) {
-    double A[36];
-    std::memcpy(A, A_in, sizeof(A));
-    double det = 1.0;
-    for (int c = 0; c < 6; ++c) {
-        int piv = c;
-        for (int r = c + 1; r < 6; ++r)
-            if (std::fabs(A[6 * r + c]) > std::fabs(A[6 * piv + c])) piv = r;
-        if (A[6 * piv + c] == 0.0) return 0.0;
-        if (piv != c) {
-            for (int k = 0; k < 6; ++k) std::swap(A[6 * c + k], A[6 * piv + k]);
-            det = -det;
-        }
-        det *= A[6 * c + c];
-        for (int r = c + 1; r < 6; ++r) {
-            double f = A[6 * r + c] / A[6 * c + c];
-            for (int k = c; k < 6; ++k) A[6 * r + k] -= f * A[6 * c + k];
-        }
-    }
-    return det;
-}
-
 // A.6  utility::TransformVector6dToMatrix4d: Rz(x2) * Ry(x1) * Rx(x0), t = x3..5
 void vec6_to_mat4(const double x[6], double* T) {
     double ca = std::cos(x[0]), sa = std::sin(x[0]);
@@ -493,8 +471,8 @@ void point_to_plane_from_corr(const double* src, const double* tgt, const double
     }
     double rhs[6], x[6];
     for (int i = 0; i < 6; ++i) rhs[i] = -JTr[i];
-    double det = det6(JTJ);
-    if (!(std::fabs(det) >= 1e-6) || !std::isfinite(det)) return;  // SolveLinearSystemPSD det check
+    // utility::SolveLinearSystemPSD with its defaults (check_det = false): x = JTJ.ldlt().solve(-JTr);
+    // a break-down of the factorisation yields the identity update.
     if (!ldlt6_solve(JTJ, rhs, x)) return;
     vec6_to_mat4(x, T);
 }

@@ -1,0 +1,103 @@
+"""The B200 processor behind the reference's plugin interface, against the reference sequence
+restated on the CPU oracle (oracle/pipeline.py)."""
+import multiprocessing
+import os
+
+import numpy as np
+import pytest
+
+from conftest import assert_transform_close
+from oracle import pipeline
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CONFIG = os.path.join(ROOT, "3d-lidar-slam_b200", "config", "lidar_config.yaml")
+
+
+def _scans(n, seed=2):
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(seed, length=10.0)
+    poses = synth.corridor_trajectory(scene, n, seed=seed, step=0.02)
+    return [synth.render_scan(scene, p, seed=50 + k).numpy() for k, p in enumerate(poses)]
+
+
+def _processor(**kw):
+    from lidar_slam_b200.plugin import DataTransfer, set_algorithm
+
+    dt = DataTransfer()
+    return set_algorithm("b200_icp", CONFIG, dt, multiprocessing.Event(), **kw), dt
+
+
+def test_reference_mode_follows_the_reference_sequence():
+    """icp_processor.py:43-119 step by step: per-cloud voxel origin, raw map, scan rows first."""
+    scans = _scans(4)
+    proc, _ = _processor(mode="reference", max_iteration=60)
+    # teacher-forced twin: the oracle rounds every stored cloud to float32 like the GPU's HBM layout
+    ref = pipeline.ReferenceSequence(max_iteration=60, maintenance="off", f32_storage=True)
+    # pure float64 sequence (what Open3D holds in memory): same poses within the stated tolerance;
+    # the 1e-6 convergence test may fire one iteration apart
+    ref64 = pipeline.ReferenceSequence(max_iteration=60, maintenance="off")
+    for k, s in enumerate(scans):
+        proc.construct_global_map(s)
+        proc.point_clouds_in_map += 1  # what ProcessPointClouds.process does after the call
+        ref.process(s)
+        ref64.process(s)
+        assert proc.point_clouds_in_map == ref.point_clouds_in_map
+        if k == 0:
+            continue
+        assert proc.last_result.iterations == ref.last_result.iterations
+        assert_transform_close(proc.previous_transformation[-1], ref.previous_transformation[-1])
+        assert abs(proc.last_result.iterations - ref64.last_result.iterations) <= 2
+        assert_transform_close(proc.previous_transformation[-1], ref64.previous_transformation[-1],
+                               rad=1e-4, metres=2e-4)
+    gm = proc.global_map
+    assert gm.shape == ref.global_map.shape == (4 * 49152, 3)
+    np.testing.assert_allclose(gm, ref.global_map, rtol=1e-5, atol=1e-4)
+    np.testing.assert_array_equal(gm[-49152:], scans[0])  # first scan is the map frame, kept verbatim at the end
+    assert len(proc.previous_transformation) == 4
+
+
+def test_resident_mode_through_the_queue():
+    """process(): queue -> projection -> construct_global_map, first-scan double increment
+    (icp_processor.py:54 + generic_point_cloud_processor.py:126), lazy global_map, reset()."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(4, length=10.0)
+    poses = synth.corridor_trajectory(scene, 3, seed=4, step=0.02)
+    proc, dt = _processor(mode="resident", max_iteration=30, map_voxel=0.05)
+    for k, p in enumerate(poses):
+        rec = synth.scan_records(synth.render_depth(scene, p, seed=70 + k)).numpy()
+        dt.pixel_depth_map_queue.put(rec)
+        proc.process()
+    assert proc.point_clouds_in_map == 4  # 3 scans + the reference's extra increment on the first
+    assert len(proc.previous_transformation) == 3
+    assert proc.last_result.fitness > 0.5
+    gm = proc.global_map
+    assert gm.ndim == 2 and gm.shape[1] == 3 and len(gm) > 3000 and gm.dtype == np.float32
+    assert proc.downsample_global_map() is gm
+    # the pose chain moves along the trajectory (constant-pose prior, icp_processor.py:106)
+    step = np.linalg.norm(proc.previous_transformation[-1][:3, 3] - proc.previous_transformation[-2][:3, 3])
+    assert 0.0 < step < 0.1
+    proc.reset_event.set()
+    proc.reset()
+    assert proc.global_map is None and proc.point_clouds_in_map == 0 and not proc.reset_event.is_set()
+    np.testing.assert_array_equal(proc.previous_transformation[-1], np.eye(4))
+
+
+def test_reference_mode_periodic_revoxelisation():
+    scans = _scans(2)
+    proc, _ = _processor(mode="reference", max_iteration=20, maintenance="voxel")
+    proc.construct_global_map(scans[0])
+    proc.point_clouds_in_map = 10  # next scan hits the count % 10 == 0 cadence (icp_processor.py:127-133)
+    proc.construct_global_map(scans[1])
+    n = len(proc.global_map)
+    assert 0 < n <= 2 * 49152
+    from oracle import cpu as orc
+
+    ref = pipeline.ReferenceSequence(max_iteration=20, maintenance="voxel")
+    ref.process(scans[0])
+    ref.point_clouds_in_map = 10
+    ref.construct_global_map(scans[1])
+    assert abs(n - len(ref.global_map)) <= 2  # 1 mm voxels: float32 vs float64 storage can split a face case
+    del orc
