@@ -1,0 +1,63 @@
+"""Oracle regression pins (tests/golden/oracle_pins.json, made by tests/golden/make_golden.py).
+They are pins of the oracle on seeded inputs — the reference offers no golden vectors (PARITY UNPINNED)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_pins.json")))
+
+
+def digest(a) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:24]
+
+
+def test_synthetic_inputs_are_reproducible(pair0):
+    src, tgt, _ = pair0
+    assert digest(src) == GOLD["inputs"]["src_sha"] and digest(tgt) == GOLD["inputs"]["tgt_sha"]
+
+
+def test_oracle_voxel_and_search_pins(pair0):
+    src, tgt, T_true = pair0
+    s64, t64 = src.astype(np.float64), tgt.astype(np.float64)
+    sd, sk, sc = cpu.voxel_downsample(s64, 0.02)
+    td, tk, _ = cpu.voxel_downsample(t64, 0.02)
+    g = GOLD["voxel_0.02"]
+    assert (len(sk), len(tk)) == (g["n_src"], g["n_tgt"])
+    assert digest(sk) == g["src_keys_sha"] and digest(sc) == g["src_counts_sha"]
+    assert digest(sd.astype(np.float32)) == g["src_centroids_f32_sha"]
+    _, fk, fc = cpu.voxel_downsample(np.concatenate([t64, cpu.transform(s64, T_true)]), 0.05, origin=[-9.0, -9.0, -9.0])
+    assert len(fk) == GOLD["fuse_0.05"]["n"] and digest(fk) == GOLD["fuse_0.05"]["keys_sha"]
+    assert digest(fc) == GOLD["fuse_0.05"]["counts_sha"]
+    idx, _ = cpu.nn_search(sd, td, 0.05)
+    assert int((idx >= 0).sum()) == GOLD["nn_0.05"]["n_corr"] and digest(idx) == GOLD["nn_0.05"]["idx_sha"]
+
+
+def test_oracle_icp_pin(pair0):
+    src, tgt, _ = pair0
+    sd, _, _ = cpu.voxel_downsample(src.astype(np.float64), 0.02)
+    td, _, _ = cpu.voxel_downsample(tgt.astype(np.float64), 0.02)
+    r = cpu.registration_icp(sd, td, 0.05, max_iteration=30)
+    g = GOLD["icp_p2p_30"]
+    np.testing.assert_allclose(r.transformation, np.array(g["T"]), rtol=0, atol=1e-12)
+    assert r.iterations == g["iterations"] and r.fitness == g["fitness"]
+    assert r.inlier_rmse == pytest.approx(g["rmse"], rel=1e-12)
+    assert digest(r.correspondence) == g["corr_sha"]
+    nrm = cpu.estimate_normals(td[:2000], 0.04, 20)
+    np.testing.assert_allclose(np.abs(nrm[:5]), np.array(GOLD["normals_first5"]), atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_against_golden_pins(engine, b2, pair0):
+    """The CUDA path against the committed fixtures (same seeded inputs)."""
+    src, tgt, _ = pair0
+    sd, sk = engine.voxel_downsample(engine.pack(src), 0.02)
+    td, _ = engine.voxel_downsample(engine.pack(tgt), 0.02)
+    g = GOLD["voxel_0.02"]
+    assert digest(sk.cpu().numpy()) == g["src_keys_sha"]
+    assert digest(sd.cpu().numpy()[:, :3]) == g["src_centroids_f32_sha"]
+    assert digest(sd.cpu().numpy()[:, 3].copy().view(np.int32)) == g["src_counts_sha"]
