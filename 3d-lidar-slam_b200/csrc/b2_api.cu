@@ -1,6 +1,7 @@
 // b2_api.cu — the C ABI (include/b2slam.h) over the kernels of this directory.
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "b2_common.cuh"
@@ -21,6 +22,11 @@ void* ws_get(Context* c, int slot, size_t bytes) {
     DevBuf& b = c->ws[slot];
     if (bytes == 0) bytes = 16;
     if (b.cap >= bytes) return b.p;
+    if (c->capturing) {
+        set_error(c, B2_ERR_CUDA, "workspace slot %d would have to grow during graph capture", slot);
+        return nullptr;
+    }
+    c->ws_generation++;
     size_t want = bytes + bytes / 4;  // headroom so slowly growing inputs do not reallocate every call
     want = (want + 255) & ~(size_t)255;
     if (b.p) {
@@ -217,6 +223,7 @@ int b2_create(int device, b2_handle* out) {
 int b2_destroy(b2_handle h) {
     CTX(h);
     cudaStreamSynchronize(c->stream);
+    if (c->scan_graph.exec) cudaGraphExecDestroy(c->scan_graph.exec);
     map_free(c);
     for (auto& b : c->ws)
         if (b.p) cudaFree(b.p);
@@ -487,17 +494,10 @@ int b2_slam_get_pose(b2_handle h, double* T) {
     return B2_OK;
 }
 
-static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
-                          const b2_icp_params* params, b2_icp_result* out, bool map_empty) {
-    const float4* scan = scan_dev;
-    if (!scan) {
-        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
-        B2_WS(c, packed, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)n);
-        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-        pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, packed);
-        B2_LAUNCH_CHECK(c);
-        scan = packed;
-    }
+// Everything of one scan step after the scan sits in the fixed device buffer `scan`:
+// down-sample -> ICP against the resident map (pose chained on the device) -> fuse.
+static int slam_body(Context* c, const float4* scan, int n, double ds_voxel, const b2_icp_params* params,
+                     bool map_empty) {
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
     if (!map_empty) {
@@ -522,6 +522,77 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
         B2_LAUNCH_CHECK(c);
     }
     B2_TRY(map_fuse(c, scan, n, nullptr, pose));
+    return B2_OK;
+}
+
+// The step is ~100 small kernels; replaying it as a CUDA graph removes the per-launch CPU cost and
+// most of the inter-kernel gap.  A graph is keyed by everything baked into its nodes (sizes,
+// parameters, workspace/map addresses); the first call with a new key runs eagerly (it sizes the
+// workspaces), the second captures, later calls replay.
+static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_voxel, const b2_icp_params* params) {
+    static const bool no_graph = getenv("B2_NO_GRAPH") != nullptr;
+    ScanGraph& sg = c->scan_graph;
+    const bool same = sg.n == n && sg.ds_voxel == ds_voxel && sg.scan == scan &&
+                      std::memcmp(&sg.params, params, sizeof(*params)) == 0 && sg.generation == c->ws_generation;
+    if (no_graph) return slam_body(c, scan, n, ds_voxel, params, false);
+    if (same && sg.exec) {
+        B2_CUDA_OK(c, cudaGraphLaunch(sg.exec, c->stream));
+        c->launches += sg.kernel_nodes;
+        return B2_OK;
+    }
+    if (!same) {  // new shape: eager run, remember the key
+        if (sg.exec) cudaGraphExecDestroy(sg.exec);
+        sg.exec = nullptr;
+        B2_TRY(slam_body(c, scan, n, ds_voxel, params, false));
+        sg.n = n; sg.ds_voxel = ds_voxel; sg.scan = scan; sg.params = *params; sg.generation = c->ws_generation;
+        return B2_OK;
+    }
+    // second call with this key: capture
+    const unsigned long long launches_before = c->launches;
+    B2_CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    c->capturing = true;
+    int rc = slam_body(c, scan, n, ds_voxel, params, false);
+    c->capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != B2_OK || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        sg.n = -1;  // do not try again with this key until it changes
+        c->launches = launches_before;
+        if (rc != B2_OK && rc != B2_ERR_CUDA) return rc;
+        return slam_body(c, scan, n, ds_voxel, params, false);
+    }
+    e = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        sg.exec = nullptr;
+        sg.n = -1;
+        c->launches = launches_before;
+        return slam_body(c, scan, n, ds_voxel, params, false);
+    }
+    sg.kernel_nodes = (int)(c->launches - launches_before);
+    c->launches = launches_before + sg.kernel_nodes;
+    B2_CUDA_OK(c, cudaGraphLaunch(sg.exec, c->stream));
+    return B2_OK;
+}
+
+static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
+                          const b2_icp_params* params, b2_icp_result* out, bool map_empty) {
+    // the scan always lands in one fixed device buffer so that the step's graph can be replayed
+    B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)n);
+    if (scan_dev) {
+        B2_CUDA_OK(c, cudaMemcpyAsync(scan, scan_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);
+        B2_LAUNCH_CHECK(c);
+    }
+    if (map_empty) B2_TRY(slam_body(c, scan, n, ds_voxel, params, true));
+    else B2_TRY(slam_body_graphed(c, scan, n, ds_voxel, params));
+    double* pose = map_pose_dev(c);
+    IcpResultDev* res = map_result_dev(c);
     if (out) {
         IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
         if (map_empty) {

@@ -37,13 +37,24 @@ struct DevBuf {
 enum WsSlot : int {
     WS_KEYS_A = 0, WS_KEYS_B, WS_VALS_A, WS_VALS_B, WS_HIST, WS_CTL, WS_SEGSTART, WS_BLOCKCNT,
     WS_BBOX, WS_PREP, WS_TMP_PTS, WS_TMP_PTS2, WS_TMP_KEYS, WS_SUMS, WS_COUNTS, WS_OFFS_A, WS_OFFS_B,
-    WS_GRID_ENTRIES, WS_GRID_PTS, WS_GRID_META, WS_ICP_STATE, WS_ICP_PARTIAL, WS_ICP_TICKET,
+    WS_GRID_ENTRIES, WS_GRID_PTS, WS_GRID_META, WS_ICP_STATE, WS_ICP_PARTIAL, WS_ICP_TICKET, WS_ICP_SYNC,
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
     WS_CORR, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu
+
+// Cached CUDA graph of one scan step (b2_api.cu) and the key it was captured for.
+struct ScanGraph {
+    cudaGraphExec_t exec = nullptr;
+    int n = -1;
+    double ds_voxel = 0.0;
+    const void* scan = nullptr;
+    b2_icp_params params{};
+    unsigned long long generation = 0;
+    int kernel_nodes = 0;
+};
 
 struct Context {
     int device = 0;
@@ -56,6 +67,9 @@ struct Context {
     int sort_passes_hint = 4;      // upper bound of 8-bit radix passes launched
     MapState* map = nullptr;
     unsigned long long launches = 0;  // kernels launched through this context
+    unsigned long long ws_generation = 0;  // bumped whenever a workspace / map buffer is (re)allocated
+    bool capturing = false;                // inside stream capture: no allocation, no synchronisation
+    ScanGraph scan_graph;
 };
 
 int set_error(Context* c, int code, const char* fmt, ...);
@@ -119,6 +133,16 @@ struct __align__(16) CellEntry {
     unsigned int cnt;        // number of points
 };
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+// Resident map with one voxel per cell (voxel edge == search radius, e.g. 5 cm / 5 cm): the centroid
+// lives INSIDE the hash entry, so a stencil probe is a single 32-byte sector and there is no second,
+// dependent load of the point.
+struct __align__(32) VoxEntry {
+    unsigned long long key;  // kEmptyKey = vacant
+    float x, y, z;           // voxel centroid (float32 of sum/n)
+    unsigned int n;          // points merged into the voxel (0 while the slot is being created)
+    unsigned int pad[2];
+};
 
 struct GridMeta {
     double origin[3];
@@ -199,6 +223,16 @@ __device__ __forceinline__ unsigned long long hash64(unsigned long long x) {
     return x;
 }
 
+// Table index hash of a packed cell key: two 32-bit multiplies + xorshift-multiply finaliser
+// (the full 64-bit murmur finaliser costs ~3x the instructions and the probe is issue-bound).
+__device__ __forceinline__ unsigned cell_hash(unsigned long long key) {
+    unsigned h = (unsigned)key * 0x9E3779B1u ^ (unsigned)(key >> 32) * 0x85EBCA77u;
+    h ^= h >> 16;
+    h *= 0x7FEB352Du;
+    h ^= h >> 15;
+    return h;
+}
+
 // pair-grid cell key: [pair:16][x:16][y:16][z:16], coordinates relative to the cloud origin
 __device__ __forceinline__ unsigned long long pair_cell_key(unsigned pair, int x, int y, int z) {
     return ((unsigned long long)pair << 48) | ((unsigned long long)(unsigned)x << 32) |
@@ -218,7 +252,7 @@ __device__ __forceinline__ int floor_div(int a, int b) {
 // Probe an open-addressing table (linear probing); returns the entry or a vacant one.
 __device__ __forceinline__ CellEntry grid_lookup(const CellEntry* __restrict__ tab, unsigned mask,
                                                  unsigned long long key) {
-    unsigned h = (unsigned)hash64(key) & mask;
+    unsigned h = cell_hash(key) & mask;
     CellEntry e;
     e.key = kEmptyKey; e.off = 0; e.cnt = 0;
 #pragma unroll 1
@@ -233,6 +267,33 @@ __device__ __forceinline__ CellEntry grid_lookup(const CellEntry* __restrict__ t
         h = (h + 1) & mask;
     }
     return e;
+}
+
+// One 256-bit load (LDG.E.256 on sm_100a) of a 32-byte-aligned record.
+__device__ __forceinline__ void ldg256(const void* p, unsigned long long& a, unsigned long long& b,
+                                       unsigned long long& c, unsigned long long& d) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+// Probe the dense voxel table: on a hit returns true and the centroid + slot of the voxel.
+__device__ __forceinline__ bool vox_lookup(const VoxEntry* __restrict__ tab, unsigned mask, unsigned long long key,
+                                           float& x, float& y, float& z, unsigned& slot) {
+    unsigned h = cell_hash(key) & mask;
+#pragma unroll 1
+    for (unsigned probe = 0; probe <= mask; ++probe) {
+        unsigned long long k, xy, zn, pad;
+        ldg256(tab + h, k, xy, zn, pad);
+        if (k == key) {
+            x = __uint_as_float((unsigned)xy);
+            y = __uint_as_float((unsigned)(xy >> 32));
+            z = __uint_as_float((unsigned)zn);
+            slot = h;
+            return (unsigned)(zn >> 32) != 0u;
+        }
+        if (k == kEmptyKey) return false;
+        h = (h + 1) & mask;
+    }
+    return false;
 }
 
 #endif  // __CUDACC__
@@ -278,7 +339,8 @@ struct GridView {
     unsigned mask;        // capacity - 1
     float4* pts;          // cell-sorted copy, w = original (per-cloud) index
     GridMeta* meta;       // [n_clouds]
-    int is_map;
+    int is_map;           // 0: pair grid, 1: resident map with slabs (brick > 1), 2: dense resident map (vox)
+    VoxEntry* vox;        // is_map == 2
 };
 int grid_build(Context* c, const float4* pts, int n_max, const int* n_dev, const int* cloud_offsets, int n_clouds,
                double cell, int slot_base, GridView* out);

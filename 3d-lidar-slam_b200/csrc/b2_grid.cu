@@ -62,7 +62,7 @@ grid_fill_kernel(const float4* __restrict__ pts, const int* __restrict__ offs, i
         unsigned kx = (unsigned)(k & ((1ull << bx) - 1ull));
         k >>= bx;
         const unsigned long long ckey = pair_cell_key((unsigned)k, (int)kx, (int)ky, (int)kz);
-        unsigned h = (unsigned)hash64(ckey) & mask;
+        unsigned h = cell_hash(ckey) & mask;
         for (unsigned probe = 0; probe <= mask; ++probe) {
             unsigned long long prev = atomicCAS(&entries[h].key, kEmptyKey, ckey);
             if (prev == kEmptyKey) {
@@ -100,6 +100,7 @@ int grid_build(Context* c, const float4* pts, int n_max, const int* n_dev, const
     out->pts = gpts;
     out->meta = meta;
     out->is_map = 0;
+    out->vox = nullptr;
     return B2_OK;
 }
 

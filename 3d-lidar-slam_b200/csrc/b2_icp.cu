@@ -18,8 +18,10 @@
 //     composes T <- dT * T in place.  Nothing returns to the host inside the loop;
 //     pairs that have converged turn later launches into no-ops.
 //
-// Algorithmic bytes of one launch (DESIGN.md §roofline): 16*Ns (queries) +
+// Algorithmic bytes of one launch (DESIGN.md §4): 16*Ns (queries) +
 // 16*sum_q cand(q) (candidate points) + 16*27*Ns (cell records) + 256*CTAs.
+#include <cstdlib>
+
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -58,7 +60,9 @@ __device__ __noinline__ void rotation_from_covariance(const double C[9], double 
                 beta += A[3 * k + q] * A[3 * k + q];
                 gamma += A[3 * k + p] * A[3 * k + q];
             }
-            if (gamma != 0.0 && fabs(gamma) > 1e-16 * sqrt(alpha * beta)) {
+            // 8 ulp: below that the columns are orthogonal to working precision (a tighter test
+            // never settles — rounding noise keeps it rotating for all 60 sweeps)
+            if (gamma != 0.0 && gamma * gamma > 3e-30 * (alpha * beta)) {
                 rotated = true;
                 double zeta = (beta - alpha) / (2.0 * gamma);
                 double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -162,21 +166,64 @@ __device__ __noinline__ bool solve6(const double* JtJ_upper /*21*/, const double
     return true;
 }
 
-__device__ void mat4_mul_inplace_left(const double U[16], double T[16]) {
-    double r[16];
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 4; ++k) s += U[4 * i + k] * T[4 * k + j];
-            r[4 * i + j] = s;
+// Polar factor of a 3x3 with positive determinant by Frobenius-scaled Newton iteration,
+// X <- (g X + (g X)^-T) / 2: when det(C) > 0 the orthogonal polar factor IS U V^T, the Umeyama
+// rotation.  Everything stays in registers; the scale factor only steers convergence, so it is
+// evaluated in float32.  Returns false (caller falls back to the Jacobi SVD) for det <= 0 — the
+// reflection / rank-deficient cases — or if the iteration does not settle.
+__device__ __forceinline__ bool polar_rotation(double a, double b, double c, double d, double e, double f, double g,
+                                               double h, double i, double* R) {
+    {
+        const double nrm = sqrt(a * a + b * b + c * c + d * d + e * e + f * f + g * g + h * h + i * i);
+        if (!(nrm > 0.0) || !isfinite(nrm)) return false;
+        const double s = 1.7320508075688772 / nrm;
+        a *= s; b *= s; c *= s; d *= s; e *= s; f *= s; g *= s; h *= s; i *= s;
+    }
+    bool ok = false;
+#pragma unroll 1
+    for (int it = 0; it < 40; ++it) {
+        const double c00 = e * i - f * h, c01 = f * g - d * i, c02 = d * h - e * g;
+        const double c10 = c * h - b * i, c11 = a * i - c * g, c12 = b * g - a * h;
+        const double c20 = b * f - c * e, c21 = c * d - a * f, c22 = a * e - b * d;
+        const double det = a * c00 + b * c01 + c * c02;
+        if (!(det > 1e-12)) return false;  // (scaled so that |X|_F = sqrt(3): an orthogonal X has det 1)
+        const double nx2 = a * a + b * b + c * c + d * d + e * e + f * f + g * g + h * h + i * i;
+        const double nc2 = c00 * c00 + c01 * c01 + c02 * c02 + c10 * c10 + c11 * c11 + c12 * c12 + c20 * c20 +
+                           c21 * c21 + c22 * c22;
+        // gamma = (|X^-T|_F / |X|_F)^(1/2), |X^-T|_F = sqrt(nc2)/det
+        const float gam = sqrtf(sqrtf((float)(nc2 / (det * det * nx2))));
+        const double ga = 0.5 * (double)gam, gb = 0.5 / ((double)gam * det);
+        const double na = ga * a + gb * c00, nb = ga * b + gb * c01, nc = ga * c + gb * c02;
+        const double nd = ga * d + gb * c10, ne = ga * e + gb * c11, nf = ga * f + gb * c12;
+        const double ng = ga * g + gb * c20, nh = ga * h + gb * c21, ni = ga * i + gb * c22;
+        const double diff = (na - a) * (na - a) + (nb - b) * (nb - b) + (nc - c) * (nc - c) + (nd - d) * (nd - d) +
+                            (ne - e) * (ne - e) + (nf - f) * (nf - f) + (ng - g) * (ng - g) + (nh - h) * (nh - h) +
+                            (ni - i) * (ni - i);
+        a = na; b = nb; c = nc; d = nd; e = ne; f = nf; g = ng; h = nh; i = ni;
+        if (diff < 1e-22) {  // quadratic convergence: the next update is below 1e-20
+            ok = true;
+            break;
         }
-    for (int i = 0; i < 16; ++i) T[i] = r[i];
+    }
+    if (!ok) return false;
+    {  // one unscaled polishing step
+        const double c00 = e * i - f * h, c01 = f * g - d * i, c02 = d * h - e * g;
+        const double c10 = c * h - b * i, c11 = a * i - c * g, c12 = b * g - a * h;
+        const double c20 = b * f - c * e, c21 = c * d - a * f, c22 = a * e - b * d;
+        const double hd = 0.5 / (a * c00 + b * c01 + c * c02);
+        R[0] = 0.5 * a + hd * c00; R[1] = 0.5 * b + hd * c01; R[2] = 0.5 * c + hd * c02;
+        R[3] = 0.5 * d + hd * c10; R[4] = 0.5 * e + hd * c11; R[5] = 0.5 * f + hd * c12;
+        R[6] = 0.5 * g + hd * c20; R[7] = 0.5 * h + hd * c21; R[8] = 0.5 * i + hd * c22;
+    }
+    return true;
 }
 
-// Evaluate one A.3 loop step from the reduced sums.  Runs on one thread.
+// Evaluate one A.3 loop step from the reduced sums.  Runs on one thread; written so that every
+// small matrix stays in registers (a single GPU thread retires roughly one dependent instruction
+// per 6-10 cycles, so the instruction count of this tail is what the iteration latency is made of).
 template <int MODE>
 __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams prm, IcpState* st, IcpResultDev* res,
-                         int* ndone) {
+                                      int* ndone) {
     const double n = MODE == 0 ? S[16] : S[28];
     const double sd2 = MODE == 0 ? S[15] : S[27];
     const double fitness = ns > 0 ? n / (double)ns : 0.0;
@@ -189,9 +236,14 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
     st->fitness = fitness;
     st->rmse = rmse;
     st->n_corr = (int)n;
+    double T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = st->T[k];
     if (done) {
         st->done = 1;
-        for (int i = 0; i < 16; ++i) res->T[i] = st->T[i];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) res->T[k] = T[k];
+        res->T[12] = 0.0; res->T[13] = 0.0; res->T[14] = 0.0; res->T[15] = 1.0;
         res->fitness = fitness;
         res->rmse = rmse;
         res->iterations = st->iter;
@@ -199,28 +251,25 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
         atomicAdd(ndone, 1);
         return;
     }
-    double U[16];
-    for (int i = 0; i < 16; ++i) U[i] = (i % 5 == 0) ? 1.0 : 0.0;
+    double U[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};  // update, 3x4
     if (n > 0) {
         if (MODE == 0) {
-            double mp[3], mq[3], C[9], R[9];
             const double inv = 1.0 / n;
-            for (int k = 0; k < 3; ++k) {
-                mp[k] = S[k] * inv;
-                mq[k] = S[3 + k] * inv;
-            }
-            for (int i = 0; i < 3; ++i)
-                for (int j = 0; j < 3; ++j) C[3 * i + j] = S[6 + 3 * i + j] * inv - mq[i] * mp[j];
-            rotation_from_covariance(C, R);
-            for (int k = 0; k < 3; ++k) {
-                mp[k] += st->pivot[k];
-                mq[k] += st->pivot[k];
-            }
-            for (int i = 0; i < 3; ++i) {
-                for (int j = 0; j < 3; ++j) U[4 * i + j] = R[3 * i + j];
-                U[4 * i + 3] = mq[i] - (R[3 * i] * mp[0] + R[3 * i + 1] * mp[1] + R[3 * i + 2] * mp[2]);
-            }
-            for (int k = 0; k < 3; ++k) st->pivot[k] = mq[k];
+            double mp0 = S[0] * inv, mp1 = S[1] * inv, mp2 = S[2] * inv;
+            double mq0 = S[3] * inv, mq1 = S[4] * inv, mq2 = S[5] * inv;
+            double C[9], R[9];
+            C[0] = S[6] * inv - mq0 * mp0;  C[1] = S[7] * inv - mq0 * mp1;  C[2] = S[8] * inv - mq0 * mp2;
+            C[3] = S[9] * inv - mq1 * mp0;  C[4] = S[10] * inv - mq1 * mp1; C[5] = S[11] * inv - mq1 * mp2;
+            C[6] = S[12] * inv - mq2 * mp0; C[7] = S[13] * inv - mq2 * mp1; C[8] = S[14] * inv - mq2 * mp2;
+            if (!polar_rotation(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], R))
+                rotation_from_covariance(C, R);
+            const double p0 = st->pivot[0], p1 = st->pivot[1], p2 = st->pivot[2];
+            mp0 += p0; mp1 += p1; mp2 += p2;
+            mq0 += p0; mq1 += p1; mq2 += p2;
+            U[0] = R[0]; U[1] = R[1]; U[2] = R[2];  U[3] = mq0 - (R[0] * mp0 + R[1] * mp1 + R[2] * mp2);
+            U[4] = R[3]; U[5] = R[4]; U[6] = R[5];  U[7] = mq1 - (R[3] * mp0 + R[4] * mp1 + R[5] * mp2);
+            U[8] = R[6]; U[9] = R[7]; U[10] = R[8]; U[11] = mq2 - (R[6] * mp0 + R[7] * mp1 + R[8] * mp2);
+            st->pivot[0] = mq0; st->pivot[1] = mq1; st->pivot[2] = mq2;
         } else {
             double rhs[6], x[6];
             for (int k = 0; k < 6; ++k) rhs[k] = -S[21 + k];
@@ -233,7 +282,15 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
             }
         }
     }
-    mat4_mul_inplace_left(U, st->T);
+    // T <- U * T for affine 3x4 blocks (the last row stays 0,0,0,1)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double u0 = U[4 * r], u1 = U[4 * r + 1], u2 = U[4 * r + 2], u3 = U[4 * r + 3];
+        st->T[4 * r + 0] = u0 * T[0] + u1 * T[4] + u2 * T[8];
+        st->T[4 * r + 1] = u0 * T[1] + u1 * T[5] + u2 * T[9];
+        st->T[4 * r + 2] = u0 * T[2] + u1 * T[6] + u2 * T[10];
+        st->T[4 * r + 3] = u0 * T[3] + u1 * T[7] + u2 * T[11] + u3;
+    }
     st->iter += 1;
     st->prev_fitness = fitness;
     st->prev_rmse = rmse;
@@ -241,29 +298,274 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
 }
 
 // ---------------------------------------------------------------------------
-// the hot kernel
+// the hot kernels
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ int warp_lower_bound_gt(int incl, int c) {
-    // smallest lane l with incl[l] > c  (incl is non-decreasing over lanes)
-    int l = 0;
-#pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-        int probe = l + step - 1;
-        int v = __shfl_sync(kFull, incl, probe & 31);
-        if (v <= c) l += step;
+// Work decomposition: a warp serves FOUR queries at a time, eight lanes each.  Lane g of a group
+// probes stencil cells {g, g+8, g+16, g+24 (<27)}: the four hash probes of a lane are issued back to
+// back (memory-level parallelism 4 per lane, 128 per warp) before any of them is consumed, and the
+// group's arg-min is a 3-step shuffle butterfly.  The group leader (lane g == 0) owns the query:
+// it loads and transforms the point, and adds the query's contribution to its private column of
+// the shared-memory accumulators, so no per-query warp-wide reduction is needed.
+//
+// Two drivers share that body:
+//   icp_iter_kernel     one launch per A.3 step, gridDim.y = pairs (batches; last CTA of a pair solves)
+//   icp_persist_kernel  one cooperative launch per registration of a single pair: the CTAs stay
+//                       resident, keep their query points in registers, and meet once per step at a
+//                       ticket barrier whose last arriver reduces, solves and publishes T — no
+//                       kernel boundary, no relaunch, immediate exit on convergence.
+#ifdef B2_TAIL_TIMING
+__device__ unsigned long long g_tail_ts[8 + 2 * 1024];
+__device__ unsigned long long g_pts[300 * 8];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define B2_TS(slot) do { if (threadIdx.x == 0) g_tail_ts[slot] = gtime(); } while (0)
+#define B2_TS_BLOCK(k) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_tail_ts[8 + 2 * blockIdx.x + (k)] = gtime(); } while (0)
+#else
+#define B2_TS(slot) do {} while (0)
+#define B2_TS_BLOCK(k) do {} while (0)
+#endif
+constexpr int kGroup = 8;
+constexpr int kLeaders = kThreads / kGroup;  // accumulator columns per CTA
+
+struct SearchArgs {
+    const CellEntry* entries;
+    const VoxEntry* vox;
+    const float4* gpts;
+    const float4* tgt_normals;
+    unsigned mask;
+    int tgt_base;
+    unsigned pair;
+    double r2;
+    int* corr_out;
+    double* d2_out;
+    int search_only;
+};
+
+// One round: the warp's four groups each register one query (p = the leader's source point, valid
+// per group) against the grid and add its normal-equation terms to column `col` of sAccL.
+template <int MODE, int KIND>
+__device__ __forceinline__ void search_round(const SearchArgs& a, const double* __restrict__ sT,
+                                             const double* __restrict__ sPivot, const GridMeta& meta, float4 p,
+                                             bool valid, int q, double (*sAccL)[kLeaders], int col) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane & (kGroup - 1);
+    const int lead = lane & ~(kGroup - 1);
+    // ---- leader: transform the query, find its cell ---------------------------------------------
+    double Px = 0.0, Py = 0.0, Pz = 0.0;
+    int cx = 0, cy = 0, cz = 0;
+    if (g == 0 && valid) {
+        const D3 P = xform_strict(sT, (double)p.x, (double)p.y, (double)p.z);
+        Px = P.x; Py = P.y; Pz = P.z;
+        cx = voxel_coord(Px, meta.origin[0], meta.cell);
+        cy = voxel_coord(Py, meta.origin[1], meta.cell);
+        cz = voxel_coord(Pz, meta.origin[2], meta.cell);
+        if (KIND == 1 && meta.brick > 1) {
+            cx = floor_div(cx, meta.brick);
+            cy = floor_div(cy, meta.brick);
+            cz = floor_div(cz, meta.brick);
+        }
     }
-    return l;
+    Px = __shfl_sync(kFull, Px, lead);
+    Py = __shfl_sync(kFull, Py, lead);
+    Pz = __shfl_sync(kFull, Pz, lead);
+    cx = __shfl_sync(kFull, cx, lead);
+    cy = __shfl_sync(kFull, cy, lead);
+    cz = __shfl_sync(kFull, cz, lead);
+
+    // ---- the group's 27 stencil cells: 4 (3 for g >= 3) per lane, probes issued together ----------
+    double best = INFINITY;
+    int best_idx = 0x7fffffff;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    if (valid) {
+        unsigned long long key[4];
+        unsigned hpos[4];
+        bool live[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = g + kGroup * k;
+            const int nx = cx + c / 9 - 1, ny = cy + (c / 3) % 3 - 1, nz = cz + c % 3 - 1;
+            if (KIND) {
+                live[k] = c < 27 && nx > -(1 << 20) && nx < (1 << 20) && ny > -(1 << 20) && ny < (1 << 20) &&
+                          nz > -(1 << 20) && nz < (1 << 20);
+                key[k] = map_cell_key(nx, ny, nz);
+            } else {
+                live[k] = c < 27 && nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
+                key[k] = pair_cell_key(a.pair, nx, ny, nz);
+            }
+            hpos[k] = cell_hash(key[k]) & a.mask;
+        }
+        if (KIND == 2) {
+            unsigned long long ek[4], exy[4], ezn[4], epad[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (live[k]) ldg256(a.vox + hpos[k], ek[k], exy[k], ezn[k], epad[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!live[k]) continue;
+                unsigned h = hpos[k];
+                while (ek[k] != key[k] && ek[k] != kEmptyKey) {  // collision chain (rare at load <= 0.5)
+                    h = (h + 1) & a.mask;
+                    ldg256(a.vox + h, ek[k], exy[k], ezn[k], epad[k]);
+                }
+                if (ek[k] == key[k] && (unsigned)(ezn[k] >> 32) != 0u) {
+                    const float x = __uint_as_float((unsigned)exy[k]);
+                    const float y = __uint_as_float((unsigned)(exy[k] >> 32));
+                    const float z = __uint_as_float((unsigned)ezn[k]);
+                    const double d2 = dist2_strict(Px, Py, Pz, (double)x, (double)y, (double)z);
+                    if (d2 < best || (d2 == best && (int)h < best_idx)) {
+                        best = d2;
+                        best_idx = (int)h;
+                        bx = x; by = y; bz = z;
+                    }
+                }
+            }
+        } else {
+            uint4 raw[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (live[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(a.entries + hpos[k]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!live[k]) continue;
+                unsigned h = hpos[k];
+                unsigned long long kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
+                while (kk != key[k] && kk != kEmptyKey) {
+                    h = (h + 1) & a.mask;
+                    raw[k] = __ldg(reinterpret_cast<const uint4*>(a.entries + h));
+                    kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
+                }
+                if (kk != key[k]) continue;
+                const unsigned off = raw[k].z;
+                const int cnt = (int)raw[k].w;
+                for (int j = 0; j < cnt; ++j) {
+                    const float4 t = __ldg(a.gpts + off + j);
+                    const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
+                    const int idx = __float_as_int(t.w);
+                    if (d2 < best || (d2 == best && idx < best_idx)) {
+                        best = d2;
+                        best_idx = idx;
+                        bx = t.x; by = t.y; bz = t.z;
+                    }
+                }
+            }
+        }
+    }
+    // ---- arg-min over the 8 lanes of the group: (d2, idx) lexicographic -----------------------------
+    double gbest = best;
+    int gidx = best_idx;
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) {
+        const double od = __shfl_xor_sync(kFull, gbest, o);
+        const int oi = __shfl_xor_sync(kFull, gidx, o);
+        if (od < gbest || (od == gbest && oi < gidx)) {
+            gbest = od;
+            gidx = oi;
+        }
+    }
+    const bool found = valid && gbest < a.r2;
+    const unsigned winners = __ballot_sync(kFull, found && best == gbest && best_idx == gidx);
+    const int wl = lead + __ffs((winners >> lead) & 0xffu) - 1;  // meaningful only when found
+    const float Qxf = __shfl_sync(kFull, bx, wl & 31);
+    const float Qyf = __shfl_sync(kFull, by, wl & 31);
+    const float Qzf = __shfl_sync(kFull, bz, wl & 31);
+    if (g != 0 || !valid) return;
+    // ---- leader: outputs + contribution of this correspondence --------------------------------------
+    if (a.corr_out) a.corr_out[q] = found ? gidx : -1;
+    if (a.d2_out) a.d2_out[q] = found ? gbest : 0.0;
+    if (a.search_only || !found) return;
+    const double Qx = Qxf, Qy = Qyf, Qz = Qzf;
+    if (MODE == 0) {
+        const double px = Px - sPivot[0], py = Py - sPivot[1], pz = Pz - sPivot[2];
+        const double qx = Qx - sPivot[0], qy = Qy - sPivot[1], qz = Qz - sPivot[2];
+        sAccL[0][col] += px;       sAccL[1][col] += py;       sAccL[2][col] += pz;
+        sAccL[3][col] += qx;       sAccL[4][col] += qy;       sAccL[5][col] += qz;
+        sAccL[6][col] += qx * px;  sAccL[7][col] += qx * py;  sAccL[8][col] += qx * pz;
+        sAccL[9][col] += qy * px;  sAccL[10][col] += qy * py; sAccL[11][col] += qy * pz;
+        sAccL[12][col] += qz * px; sAccL[13][col] += qz * py; sAccL[14][col] += qz * pz;
+        sAccL[15][col] += gbest;
+        sAccL[16][col] += 1.0;
+    } else {
+        const float4 nq = __ldg(a.tgt_normals + a.tgt_base + gidx);
+        const double nx = nq.x, ny = nq.y, nz = nq.z;
+        double J[6];
+        J[0] = Py * nz - Pz * ny;
+        J[1] = Pz * nx - Px * nz;
+        J[2] = Px * ny - Py * nx;
+        J[3] = nx; J[4] = ny; J[5] = nz;
+        const double r = (Px - Qx) * nx + (Py - Qy) * ny + (Pz - Qz) * nz;
+        int t = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 6; ++j) sAccL[t++][col] += J[i] * J[j];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sAccL[21 + i][col] += J[i] * r;
+        sAccL[27][col] += gbest;
+        sAccL[28][col] += 1.0;
+    }
 }
 
-template <int MODE, int IS_MAP>
+// CTA-wide fixed-order fold of the leader columns into one partial per term (warp w: terms w, w+16).
+template <int NT>
+__device__ __forceinline__ void cta_fold(double (*sAccL)[kLeaders], double* __restrict__ out) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int t = w; t < NT; t += kWarps) {
+        double s = 0.0;
+#pragma unroll
+        for (int c0 = 0; c0 < kLeaders; c0 += 32) s += sAccL[t][c0 + lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+        if (lane == 0) out[t] = s;
+    }
+}
+
+// Fixed-order sum of the per-CTA partials (all loads of a thread in flight before the first add).
+template <int NT>
+__device__ __forceinline__ void grid_fold(const double* __restrict__ partial, int n_cta, double (*sRed)[kTerms],
+                                          double* __restrict__ sSum) {
+    constexpr int kParts = kThreads / 32;
+    constexpr int kMaxPer = (2 * kSMs + kParts - 1) / kParts;
+    const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
+    double s = 0.0;
+    if (j < NT) {
+        if (n_cta <= 2 * kSMs) {
+            double v[kMaxPer];
+#pragma unroll
+            for (int k = 0; k < kMaxPer; ++k) {
+                const int b = part + k * kParts;
+                v[k] = b < n_cta ? __ldcg(partial + (size_t)b * kTerms + j) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxPer; ++k) s += v[k];
+        } else {
+            for (int b = part; b < n_cta; b += kParts) s += __ldcg(partial + (size_t)b * kTerms + j);
+        }
+    }
+    sRed[part][j] = s;
+    __syncthreads();
+    if (threadIdx.x < kTerms) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < kParts; ++k) t += sRed[k][threadIdx.x];
+        sSum[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+template <int MODE, int KIND>  // KIND 0: pair grid, 1: resident map with slabs, 2: dense resident map
 __global__ void __launch_bounds__(kThreads, 2)
 icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs, const int* __restrict__ ns_dev,
                 int ns_max, const CellEntry* __restrict__ entries, unsigned mask,
-                const float4* __restrict__ gpts, const GridMeta* __restrict__ metas,
-                const float4* __restrict__ tgt_normals, const int* __restrict__ tgt_offs, IcpParams prm,
-                IcpState* __restrict__ states, double* __restrict__ partial, int* __restrict__ tickets,
-                IcpResultDev* __restrict__ results, int* __restrict__ corr_out, int* __restrict__ ndone,
-                double* __restrict__ d2_out, int search_only) {
+                const float4* __restrict__ gpts, const VoxEntry* __restrict__ vox,
+                const GridMeta* __restrict__ metas, const float4* __restrict__ tgt_normals,
+                const int* __restrict__ tgt_offs, IcpParams prm, IcpState* __restrict__ states,
+                double* __restrict__ partial, int* __restrict__ tickets, IcpResultDev* __restrict__ results,
+                int* __restrict__ corr_out, int* __restrict__ ndone, double* __restrict__ d2_out,
+                int search_only) {
+    constexpr int NT = MODE == 0 ? 17 : 29;  // live accumulator terms
     const int pair = blockIdx.y;
     IcpState* st = states + pair;
     if (st->done) return;
@@ -271,16 +573,16 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     __shared__ double sT[12];
     __shared__ double sPivot[3];
     __shared__ GridMeta sMeta;
-    __shared__ double sVals[kWarps][16];
-    __shared__ double sAcc[kWarps][kTerms];
+    __shared__ double sAccL[NT][kLeaders];
     __shared__ double sRed[kThreads / 32][kTerms];
+    __shared__ double sSum[kTerms];
     __shared__ int sLast;
 
+    B2_TS_BLOCK(0);
     if (threadIdx.x < 12) sT[threadIdx.x] = st->T[threadIdx.x];
     if (threadIdx.x < 3) sPivot[threadIdx.x] = st->pivot[threadIdx.x];
-    if (threadIdx.x == 0) sMeta = metas[IS_MAP ? 0 : pair];
-    __syncthreads();
-
+    if (threadIdx.x == 0) sMeta = metas[KIND ? 0 : pair];
+    for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
     int sb, se;
     if (src_offs) {
         sb = src_offs[pair];
@@ -289,182 +591,169 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
         sb = 0;
         se = ns_dev ? min(*ns_dev, ns_max) : ns_max;
     }
-    const int tgt_base = tgt_offs ? tgt_offs[pair] : 0;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double r2 = dmul(prm.max_corr, prm.max_corr);
-    const double cell = sMeta.cell;
-    const int brick = sMeta.brick;
-    const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
+    __syncthreads();
 
-    // Which product this lane accumulates: term = vals[ia] * vals[ib].
-    // vals layout p2p: 0:1 1..3:P' 4..6:Q' 7:d2   p2l: 0:1 1..6:J 7:r 8:d2
-    int ia = 0, ib = 0;
-    if (MODE == 0) {
-        if (lane < 3) ia = 1 + lane;
-        else if (lane < 6) ia = 4 + (lane - 3);
-        else if (lane < 15) { ia = 4 + (lane - 6) / 3; ib = 1 + (lane - 6) % 3; }
-        else if (lane == 15) ia = 7;
-        else if (lane == 16) ia = 0;
-        else ia = -1;
-    } else {
-        if (lane < 21) {
-            int t = lane, i = 0;
-            while (t >= 6 - i) { t -= 6 - i; ++i; }
-            ia = 1 + i;
-            ib = 1 + i + t;
-        } else if (lane < 27) { ia = 1 + (lane - 21); ib = 7; }
-        else if (lane == 27) ia = 8;
-        else if (lane == 28) ia = 0;
-        else ia = -1;
-    }
-    double acc = 0.0;
+    SearchArgs a;
+    a.entries = entries; a.vox = vox; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
+    a.tgt_base = tgt_offs ? tgt_offs[pair] : 0;
+    a.pair = (unsigned)pair;
+    a.r2 = dmul(prm.max_corr, prm.max_corr);
+    a.corr_out = corr_out; a.d2_out = d2_out; a.search_only = search_only;
 
-    const int warp_global = blockIdx.x * kWarps + w;
-    const int warp_stride = gridDim.x * kWarps;
-    for (int q = sb + warp_global; q < se; q += warp_stride) {
-        const float4 p = __ldg(src + q);
-        const D3 P = xform_strict(sT, (double)p.x, (double)p.y, (double)p.z);
-        int cx = voxel_coord(P.x, sMeta.origin[0], cell);
-        int cy = voxel_coord(P.y, sMeta.origin[1], cell);
-        int cz = voxel_coord(P.z, sMeta.origin[2], cell);
-        if (IS_MAP && brick > 1) {
-            cx = floor_div(cx, brick);
-            cy = floor_div(cy, brick);
-            cz = floor_div(cz, brick);
-        }
-        unsigned off = 0;
-        int cnt = 0;
-        if (lane < 27) {
-            const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-            bool ok;
-            unsigned long long key;
-            if (IS_MAP) {
-                ok = nx > -(1 << 20) && nx < (1 << 20) && ny > -(1 << 20) && ny < (1 << 20) && nz > -(1 << 20) &&
-                     nz < (1 << 20);
-                key = map_cell_key(nx, ny, nz);
-            } else {
-                ok = nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
-                key = pair_cell_key((unsigned)pair, nx, ny, nz);
-            }
-            if (ok) {
-                const CellEntry e = grid_lookup(entries, mask, key);
-                if (e.key == key) {
-                    off = e.off;
-                    cnt = (int)e.cnt;
-                }
-            }
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int v = __shfl_up_sync(kFull, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const int total = __shfl_sync(kFull, incl, 31);
-        const int excl = incl - cnt;
-
-        double best = INFINITY;
-        int best_idx = 0x7fffffff;
-        float bx = 0.f, by = 0.f, bz = 0.f;
-        for (int c0 = 0; c0 < total; c0 += 32) {
-            const int cnd = c0 + lane;
-            const int owner = warp_lower_bound_gt(incl, cnd);
-            const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-            const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-            if (cnd < total) {
-                const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                const double d2 = dist2_strict(P.x, P.y, P.z, (double)t.x, (double)t.y, (double)t.z);
-                const int idx = __float_as_int(t.w);
-                if (d2 < best || (d2 == best && idx < best_idx)) {
-                    best = d2;
-                    best_idx = idx;
-                    bx = t.x; by = t.y; bz = t.z;
-                }
-            }
-        }
-        // warp argmin over (d2, idx): d2 >= 0 so its bit pattern orders like the value
-        const unsigned long long bits = (unsigned long long)__double_as_longlong(best);
-        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
-        const unsigned mhi = __reduce_min_sync(kFull, hi);
-        const unsigned mlo = __reduce_min_sync(kFull, hi == mhi ? lo : 0xffffffffu);
-        const bool tie = hi == mhi && lo == mlo;
-        const int midx = (int)__reduce_min_sync(kFull, tie ? (unsigned)best_idx : 0x7fffffffu);
-        const unsigned win = __ballot_sync(kFull, tie && best_idx == midx);
-        const int wl = __ffs(win) - 1;
-        const double wbest = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-        const bool found = total > 0 && wbest < r2;
-        if (corr_out && lane == 0) corr_out[q] = found ? midx : -1;
-        if (d2_out && lane == 0) d2_out[q] = found ? wbest : 0.0;
-        if (search_only) continue;
-        if (found) {  // warp-uniform
-            const double Qx = (double)__shfl_sync(kFull, bx, wl);
-            const double Qy = (double)__shfl_sync(kFull, by, wl);
-            const double Qz = (double)__shfl_sync(kFull, bz, wl);
-            if (MODE == 0) {
-                if (lane == 0) {
-                    double* v = sVals[w];
-                    v[0] = 1.0;
-                    v[1] = P.x - sPivot[0]; v[2] = P.y - sPivot[1]; v[3] = P.z - sPivot[2];
-                    v[4] = Qx - sPivot[0];  v[5] = Qy - sPivot[1];  v[6] = Qz - sPivot[2];
-                    v[7] = wbest;
-                }
-            } else {
-                if (lane == 0) {
-                    const float4 nq = __ldg(tgt_normals + tgt_base + midx);
-                    const double nx = nq.x, ny = nq.y, nz = nq.z;
-                    double* v = sVals[w];
-                    v[0] = 1.0;
-                    v[1] = P.y * nz - P.z * ny;
-                    v[2] = P.z * nx - P.x * nz;
-                    v[3] = P.x * ny - P.y * nx;
-                    v[4] = nx; v[5] = ny; v[6] = nz;
-                    v[7] = (P.x - Qx) * nx + (P.y - Qy) * ny + (P.z - Qz) * nz;
-                    v[8] = wbest;
-                }
-            }
-            __syncwarp();
-            if (ia >= 0) acc += sVals[w][ia] * sVals[w][ib];
-            __syncwarp();
-        }
+    const int lane = threadIdx.x & 31;
+    const int col = threadIdx.x / kGroup;
+    // queries are dealt to groups round-robin over (round, CTA, group) so every CTA gets the same load
+    const int groups_total = gridDim.x * kLeaders;
+    const int warp_first = blockIdx.x * kLeaders + col - (lane >> 3);
+    for (int q0 = sb + warp_first; q0 < se; q0 += groups_total) {  // warp-uniform trip count
+        const int q = q0 + (lane >> 3);
+        const bool valid = q < se;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
+        search_round<MODE, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
     }
     if (search_only) return;
 
-    // CTA reduction in a fixed order
-    sAcc[w][lane] = acc;
     __syncthreads();
-    if (threadIdx.x < kTerms) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < kWarps; ++k) s += sAcc[k][threadIdx.x];
-        partial[((size_t)pair * gridDim.x + blockIdx.x) * kTerms + threadIdx.x] = s;
-    }
-    __threadfence();
+    B2_TS_BLOCK(1);
+    cta_fold<NT>(sAccL, partial + ((size_t)pair * gridDim.x + blockIdx.x) * kTerms);
     __syncthreads();
     if (threadIdx.x == 0) {
+        // one gpu-scope fence by the signalling thread: the CTA barrier above made every warp's
+        // partial visible to it, and the fence is cumulative
+        __threadfence();
         int t = atomicAdd(&tickets[pair], 1);
         sLast = (t == (int)gridDim.x - 1);
     }
     __syncthreads();
     if (!sLast) return;
-    __threadfence();
-    {
-        const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
-        double s = 0.0;
-        for (int b = part; b < (int)gridDim.x; b += kThreads / 32)
-            s += __ldcg(partial + ((size_t)pair * gridDim.x + b) * kTerms + j);
-        sRed[part][j] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < kTerms) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < kThreads / 32; ++k) s += sRed[k][threadIdx.x];
-        sAcc[0][threadIdx.x] = s;
-    }
-    __syncthreads();
+    B2_TS(0);
+    grid_fold<NT>(partial + (size_t)pair * gridDim.x * kTerms, (int)gridDim.x, sRed, sSum);
+    B2_TS(1);
     if (threadIdx.x == 0) {
         tickets[pair] = 0;
-        icp_step<MODE>(sAcc[0], se - sb, prm, st, results + pair, ndone);
+        icp_step<MODE>(sSum, se - sb, prm, st, results + pair, ndone);
+    }
+    B2_TS(2);
+}
+
+// ---- persistent single-pair driver ------------------------------------------------------------------
+struct PersistSync {
+    unsigned int ticket;  // cumulative CTA arrivals
+    unsigned int epoch;   // steps published so far
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+constexpr int kPersistRounds = 2;  // query points a group keeps in registers across steps
+
+template <int MODE, int KIND>
+__global__ void __launch_bounds__(kThreads, 2)
+icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
+                   const CellEntry* __restrict__ entries, unsigned mask, const float4* __restrict__ gpts,
+                   const VoxEntry* __restrict__ vox, const GridMeta* __restrict__ metas,
+                   const float4* __restrict__ tgt_normals, IcpParams prm, IcpState* __restrict__ st,
+                   double* __restrict__ partial, PersistSync* __restrict__ sync, IcpResultDev* __restrict__ results,
+                   int* __restrict__ corr_out, int* __restrict__ ndone) {
+    constexpr int NT = MODE == 0 ? 17 : 29;
+    __shared__ double sT[12];
+    __shared__ double sPivot[3];
+    __shared__ GridMeta sMeta;
+    __shared__ double sAccL[NT][kLeaders];
+    __shared__ double sRed[kThreads / 32][kTerms];
+    __shared__ double sSum[kTerms];
+    __shared__ int sFlag;  // 1: this CTA was the last arriver; after the barrier: done flag
+
+    const int se = ns_dev ? min(*ns_dev, ns_max) : ns_max;
+    if (threadIdx.x < 12) sT[threadIdx.x] = st->T[threadIdx.x];
+    if (threadIdx.x < 3) sPivot[threadIdx.x] = st->pivot[threadIdx.x];
+    if (threadIdx.x == 0) sMeta = metas[0];
+
+    SearchArgs a;
+    a.entries = entries; a.vox = vox; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
+    a.tgt_base = 0;
+    a.pair = 0u;
+    a.r2 = dmul(prm.max_corr, prm.max_corr);
+    a.corr_out = corr_out; a.d2_out = nullptr; a.search_only = 0;
+
+    const int lane = threadIdx.x & 31;
+    const int col = threadIdx.x / kGroup;
+    const bool leader = (lane & (kGroup - 1)) == 0;
+    const int groups_total = gridDim.x * kLeaders;
+    const int warp_first = blockIdx.x * kLeaders + col - (lane >> 3);
+    // the queries of a group do not change between steps: keep the first rounds in registers
+    float4 pq[kPersistRounds];
+#pragma unroll
+    for (int r = 0; r < kPersistRounds; ++r) {
+        const int q = warp_first + r * groups_total + (lane >> 3);
+        pq[r] = (leader && q < se) ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const unsigned n_cta = gridDim.x;
+
+    for (unsigned step = 0;; ++step) {
+#ifdef B2_TAIL_TIMING
+#define B2_PTS(k) do { if (step == 3 && threadIdx.x == 0 && blockIdx.x < 300) g_pts[blockIdx.x * 8 + (k)] = gtime(); } while (0)
+#else
+#define B2_PTS(k) do {} while (0)
+#endif
+        B2_PTS(0);
+        for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
+        __syncthreads();  // sT / sPivot / sMeta of this step and the zeroed accumulators are visible
+#pragma unroll
+        for (int r = 0; r < kPersistRounds; ++r) {
+            const int q0 = warp_first + r * groups_total;
+            if (q0 < se) {
+                const int q = q0 + (lane >> 3);
+                search_round<MODE, KIND>(a, sT, sPivot, sMeta, pq[r], q < se, q, sAccL, col);
+            }
+        }
+        for (int q0 = warp_first + kPersistRounds * groups_total; q0 < se; q0 += groups_total) {
+            const int q = q0 + (lane >> 3);
+            const bool valid = q < se;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (leader && valid) p = __ldg(src + q);
+            search_round<MODE, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+        }
+        __syncthreads();
+        B2_PTS(1);
+        cta_fold<NT>(sAccL, partial + (size_t)blockIdx.x * kTerms);
+        __syncthreads();
+        B2_PTS(2);
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned t = atomicAdd(&sync->ticket, 1u);
+            sFlag = (t == (step + 1) * n_cta - 1);
+        }
+        __syncthreads();
+        B2_PTS(3);
+        if (sFlag) {  // last arriver of this step: every partial is visible
+            __threadfence();
+            grid_fold<NT>(partial, (int)n_cta, sRed, sSum);
+            B2_PTS(4);
+            if (threadIdx.x == 0) {
+                icp_step<MODE>(sSum, se, prm, st, results, ndone);
+                B2_PTS(5);
+                __threadfence();
+                st_release_u32(&sync->epoch, step + 1);
+            }
+        } else if (threadIdx.x == 0) {
+            while (ld_acquire_u32(&sync->epoch) < step + 1) __nanosleep(40);
+        }
+        __syncthreads();
+        B2_PTS(6);
+        // pick up the published state (written by another CTA: bypass L1)
+        if (threadIdx.x < 12) sT[threadIdx.x] = __ldcg(&st->T[threadIdx.x]);
+        if (threadIdx.x < 3) sPivot[threadIdx.x] = __ldcg(&st->pivot[threadIdx.x]);
+        if (threadIdx.x == 32) sFlag = __ldcg(&st->done);
+        __syncthreads();
+        if (sFlag) break;
     }
 }
 
@@ -501,15 +790,15 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                  double* partial, int* tickets, IcpResultDev* res, int* corr, int* ndone, double* d2_out,
                  int search_only) {
     icp_iter_kernel<MODE, IS_MAP><<<grid, kThreads, 0, c->stream>>>(src, src_offs, ns_dev, ns_max, g.entries, g.mask,
-                                                                   g.pts, g.meta, nrm, tgt_offs, prm, st, partial,
+                                                                   g.pts, g.vox, g.meta, nrm, tgt_offs, prm, st, partial,
                                                                    tickets, res, corr, ndone, d2_out, search_only);
 }
 
 // Candidate census of the resident-map stencil (the data-dependent term of the byte model).
 __global__ void __launch_bounds__(256)
 stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __restrict__ T,
-                     const CellEntry* __restrict__ entries, unsigned mask, const GridMeta* __restrict__ meta,
-                     unsigned long long* __restrict__ total) {
+                     const CellEntry* __restrict__ entries, const VoxEntry* __restrict__ vox, unsigned mask,
+                     const GridMeta* __restrict__ meta, unsigned long long* __restrict__ total) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (q >= ns) return;
@@ -529,19 +818,56 @@ stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __res
     if (lane < 27) {
         const int nx = cx + lane / 9 - 1, ny = cy + (lane / 3) % 3 - 1, nz = cz + lane % 3 - 1;
         const unsigned long long key = map_cell_key(nx, ny, nz);
-        const CellEntry e = grid_lookup(entries, mask, key);
-        if (e.key == key) cnt = e.cnt;
+        if (vox) {
+            float x, y, z;
+            unsigned slot;
+            cnt = vox_lookup(vox, mask, key, x, y, z, slot) ? 1u : 0u;
+        } else {
+            const CellEntry e = grid_lookup(entries, mask, key);
+            if (e.key == key) cnt = e.cnt;
+        }
     }
     cnt = __reduce_add_sync(kFull, cnt);
     if (lane == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
+}
+
+template <int MODE, int KIND>
+int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max, const GridView& g,
+                   const float4* nrm, const IcpParams& prm, IcpState* st, double* partial, PersistSync* psync,
+                   IcpResultDev* res, int* corr, int* ndone) {
+    static int max_ctas = 0;  // co-resident CTAs of this instantiation (cooperative launch limit)
+    if (max_ctas == 0) {
+        int per_sm = 0, sms = 0;
+        B2_CUDA_OK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_persist_kernel<MODE, KIND>, kThreads, 0));
+        B2_CUDA_OK(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        max_ctas = per_sm * sms;
+        if (max_ctas < 1) return set_error(c, B2_ERR_CUDA, "persistent ICP kernel cannot be made resident");
+    }
+    int grid = div_up(ns_max, kLeaders);  // one query per 8-lane group when it fits
+    if (grid > max_ctas) grid = max_ctas;
+    if (grid > 2 * kSMs) grid = 2 * kSMs;
+    if (grid < 1) grid = 1;
+    const CellEntry* entries = g.entries;
+    unsigned mask = g.mask;
+    const float4* gpts = g.pts;
+    const VoxEntry* vox = g.vox;
+    const GridMeta* meta = g.meta;
+    IcpParams prm_v = prm;
+    void* args[] = {(void*)&src, (void*)&ns_dev, (void*)&ns_max, (void*)&entries, (void*)&mask, (void*)&gpts,
+                    (void*)&vox, (void*)&meta, (void*)&nrm, (void*)&prm_v, (void*)&st, (void*)&partial,
+                    (void*)&psync, (void*)&res, (void*)&corr, (void*)&ndone};
+    B2_CUDA_OK(c, cudaLaunchCooperativeKernel((const void*)icp_persist_kernel<MODE, KIND>, dim3(grid), dim3(kThreads),
+                                              args, 0, c->stream));
+    c->launches++;
+    return B2_OK;
 }
 
 }  // namespace
 
 int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev, const GridView& g,
                       unsigned long long* total_dev) {
-    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.mask,
-                                                                                  g.meta, total_dev);
+    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.is_map == 2 ? g.vox : nullptr,
+                                                                                  g.mask, g.meta, total_dev);
     B2_LAUNCH_CHECK(c);
     return B2_OK;
 }
@@ -567,7 +893,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     if (!(prm.max_corr > 0.0)) return set_error(c, B2_ERR_INVALID, "max_correspondence_distance must be > 0");
     const int gx = icp_grid_x(ns_max, n_pairs);
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
-    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)gx * n_pairs);
+    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > 2 * kSMs ? gx : 2 * kSMs) * n_pairs);
     B2_WS(c, tickets, int, WS_ICP_TICKET, sizeof(int) * ((size_t)n_pairs + 1));
     int* ndone = tickets + n_pairs;
     icp_init_kernel<<<div_up(n_pairs, 128), 128, 0, c->stream>>>(src, src_offsets, ns_dev, ns_max, init_dev, 16,
@@ -575,29 +901,95 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     B2_LAUNCH_CHECK(c);
     dim3 g(gx, n_pairs);
     const int launches = search_only ? 1 : prm.max_iter + 1;
-    int* host_done = (int*)c->host_mailbox + 512;  // scratch word in the pinned mailbox
-    for (int it = 0; it < launches; ++it) {
+    // (opt-in: on B200 the software grid barrier + solve of a step costs more than a kernel boundary)
+    static const bool persist = getenv("B2_PERSIST") != nullptr;
+    if (persist && n_pairs == 1 && !src_offsets && !search_only && !d2_out && !c->capturing) {
+        // single registration: one cooperative launch runs the whole A.3 loop
+        B2_WS(c, psync, PersistSync, WS_ICP_SYNC, sizeof(PersistSync));
+        B2_CUDA_OK(c, cudaMemsetAsync(psync, 0, sizeof(PersistSync), c->stream));
+        int rc = B2_OK;
         if (prm.mode == 0) {
-            if (grid.is_map)
-                launch_iter<0, 1>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states,
-                                  partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);
-            else
-                launch_iter<0, 0>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states,
-                                  partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);
+            if (grid.is_map == 2) rc = launch_persist<0, 2>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
+            else if (grid.is_map == 1) rc = launch_persist<0, 1>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
+            else rc = launch_persist<0, 0>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
         } else {
-            if (grid.is_map)
-                launch_iter<1, 1>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states,
-                                  partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);
-            else
-                launch_iter<1, 0>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states,
-                                  partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);
+            if (grid.is_map == 2) rc = launch_persist<1, 2>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
+            else if (grid.is_map == 1) rc = launch_persist<1, 1>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
+            else rc = launch_persist<1, 0>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
         }
+#ifdef B2_TAIL_TIMING
+        if (getenv("B2_TIMING")) {
+            cudaStreamSynchronize(c->stream);
+            static unsigned long long h[300 * 8];
+            cudaMemcpyFromSymbol(h, g_pts, sizeof(h));
+            int nb = div_up(ns_max, kLeaders); if (nb > 296) nb = 296;
+            unsigned long long t0 = ~0ull; for (int b = 0; b < nb; ++b) if (h[b * 8] < t0) t0 = h[b * 8];
+            unsigned long long mx[7] = {0}, mn[7]; for (int k = 0; k < 7; ++k) mn[k] = ~0ull;
+            for (int b = 0; b < nb; ++b) for (int k = 0; k < 7; ++k) { unsigned long long v = h[b * 8 + k]; if (!v) continue; v -= t0; if (v > mx[k]) mx[k] = v; if (v < mn[k]) mn[k] = v; }
+            fprintf(stderr, "[b2 persist step3 ns] start %llu..%llu | main done %llu..%llu | folded %llu..%llu | ticketed %llu..%llu | grid-fold %llu | step %llu | released %llu..%llu\n",
+                    mn[0], mx[0], mn[1], mx[1], mn[2], mx[2], mn[3], mx[3], mx[4], mx[5], mn[6], mx[6]);
+        }
+#endif
+        return rc;
+    }
+    int* host_done = (int*)c->host_mailbox + 512;  // scratch word in the pinned mailbox
+    // B2_TIMING=1: bracket every launch with CUDA events and print the per-launch device times
+    static const bool timing_env = getenv("B2_TIMING") != nullptr;
+    const bool timing = timing_env && !c->capturing;
+    std::vector<cudaEvent_t> evs;
+    if (timing) {
+        evs.resize(launches + 1);
+        for (auto& e : evs) cudaEventCreate(&e);
+        cudaEventRecord(evs[0], c->stream);
+    }
+    for (int it = 0; it < launches; ++it) {
+#define B2_ICP_LAUNCH(M, K)                                                                                   \
+    launch_iter<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
+                      tickets, results_dev, corr_out, ndone, d2_out, search_only)
+        if (prm.mode == 0) {
+            if (grid.is_map == 2) B2_ICP_LAUNCH(0, 2);
+            else if (grid.is_map == 1) B2_ICP_LAUNCH(0, 1);
+            else B2_ICP_LAUNCH(0, 0);
+        } else {
+            if (grid.is_map == 2) B2_ICP_LAUNCH(1, 2);
+            else if (grid.is_map == 1) B2_ICP_LAUNCH(1, 1);
+            else B2_ICP_LAUNCH(1, 0);
+        }
+#undef B2_ICP_LAUNCH
         B2_LAUNCH_CHECK(c);
-        if (check_every > 0 && !search_only && (it + 1) % check_every == 0 && it + 1 < launches) {
+        if (timing) cudaEventRecord(evs[it + 1], c->stream);
+        if (check_every > 0 && !search_only && !timing && (it + 1) % check_every == 0 && it + 1 < launches) {
             B2_CUDA_OK(c, cudaMemcpyAsync(host_done, ndone, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
             B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
             if (*host_done >= n_pairs) break;
         }
+    }
+    if (timing) {
+        cudaStreamSynchronize(c->stream);
+        fprintf(stderr, "[b2 timing] icp launches (us):");
+        for (int it = 0; it < launches; ++it) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, evs[it], evs[it + 1]);
+            fprintf(stderr, " %.1f", ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+#ifdef B2_TAIL_TIMING
+        {
+            static unsigned long long h[8 + 2 * 1024];
+            cudaMemcpyFromSymbol(h, g_tail_ts, sizeof(h));
+            unsigned long long t0 = ~0ull, tmain_min = ~0ull, tmain_max = 0, tstart_max = 0;
+            for (int b = 0; b < gx && b < 1024; ++b) {
+                if (h[8 + 2 * b] < t0) t0 = h[8 + 2 * b];
+                if (h[8 + 2 * b] > tstart_max) tstart_max = h[8 + 2 * b];
+                if (h[8 + 2 * b + 1] < tmain_min) tmain_min = h[8 + 2 * b + 1];
+                if (h[8 + 2 * b + 1] > tmain_max) tmain_max = h[8 + 2 * b + 1];
+            }
+            fprintf(stderr, "[b2 tail] last launch (ns from first CTA start): last CTA start %llu | main done min %llu max %llu | "
+                            "last-CTA: ticket won %llu, reduced %llu, step done %llu\n",
+                    tstart_max - t0, tmain_min - t0, tmain_max - t0, h[0] - t0, h[1] - t0, h[2] - t0);
+        }
+#endif
+        for (auto& e : evs) cudaEventDestroy(e);
     }
     return B2_OK;
 }

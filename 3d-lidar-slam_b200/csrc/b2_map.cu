@@ -15,6 +15,9 @@
 //             (first `cnt` slots used), w = slab position  -> what ICP reads.
 //   acc     : [capacity * brick^3] (sum x, sum y, sum z, n) in fp64 -> exact merge.
 //   lut/lid : per-cell voxel-local-id <-> slab-slot maps (bytes).
+//   brick == 1 (voxel edge == search radius, BASELINE config 2): the cell IS the voxel, and the
+//             table degenerates to 32-byte VoxEntry {key, centroid, n} records — a stencil probe of
+//             the ICP kernel is then one LDG.256 with no dependent second load.
 //
 // Fusion of a scan = voxel_downsample(T * scan, voxel, origin) [b2_voxel.cu]
 // followed by map_merge_kernel: one thread per UNIQUE scan voxel, so a voxel is
@@ -31,7 +34,8 @@ struct MapState {
     double origin[3] = {0, 0, 0};
     int brick = 1, cap_slots = 1, lut_stride = 16;
     unsigned capacity = 0;
-    CellEntry* entries = nullptr;
+    CellEntry* entries = nullptr;   // brick > 1
+    VoxEntry* vox = nullptr;        // brick == 1: dense table, centroid inside the entry
     unsigned char* lut = nullptr;   // [capacity * lut_stride]  voxel-local id -> slot + 1
     unsigned char* lid = nullptr;   // [capacity * cap_slots]   slot -> voxel-local id
     float4* cent = nullptr;
@@ -84,7 +88,7 @@ map_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums,
     }
     const int local = ((kx - cx * brick) * brick + (ky - cy * brick)) * brick + (kz - cz * brick);
     const unsigned long long ckey = map_cell_key(cx, cy, cz);
-    unsigned h = (unsigned)hash64(ckey) & mask;
+    unsigned h = cell_hash(ckey) & mask;
     bool placed = false;
     for (unsigned probe = 0; probe < 4096u; ++probe) {
         unsigned long long prev = atomicCAS(&entries[h].key, kEmptyKey, ckey);
@@ -140,6 +144,100 @@ map_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums,
     cpt.z = (float)ddiv(sz, n);
     cpt.w = __int_as_float((int)pos);
     cent[pos] = cpt;
+}
+
+__global__ void vox_clear_kernel(VoxEntry* __restrict__ vox, unsigned capacity) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= capacity) return;
+    VoxEntry e;
+    e.key = kEmptyKey;
+    e.x = e.y = e.z = 0.f;
+    e.n = 0;
+    e.pad[0] = e.pad[1] = 0;
+    vox[i] = e;
+}
+
+// brick == 1: one thread per unique scan voxel; the voxel's slot is found / created with a CAS on the
+// key, everything else is exclusive to this thread.
+__global__ void __launch_bounds__(kBlock)
+vox_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums, const SortCtl* __restrict__ ctl,
+                 VoxEntry* __restrict__ vox, unsigned mask, double* __restrict__ acc,
+                 long long* __restrict__ counters, unsigned long long max_cells, int* __restrict__ dev_status) {
+    const int j = blockIdx.x * kBlock + threadIdx.x;
+    if (j >= ctl->nseg) return;
+    const int kx = keys3[3 * j], ky = keys3[3 * j + 1], kz = keys3[3 * j + 2];
+    const int lim = (1 << 20) - 2;
+    if (kx < -lim || kx > lim || ky < -lim || ky > lim || kz < -lim || kz > lim) {
+        atomicCAS(dev_status, 0, B2_ERR_KEY_RANGE);
+        return;
+    }
+    const unsigned long long ckey = map_cell_key(kx, ky, kz);
+    unsigned h = cell_hash(ckey) & mask;
+    bool fresh = false, placed = false;
+    for (unsigned probe = 0; probe < 4096u; ++probe) {
+        unsigned long long prev = atomicCAS(&vox[h].key, kEmptyKey, ckey);
+        if (prev == kEmptyKey) {
+            unsigned long long cells = (unsigned long long)atomicAdd((unsigned long long*)&counters[0], 1ull) + 1ull;
+            if (cells > max_cells) atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+            atomicAdd((unsigned long long*)&counters[1], 1ull);
+            fresh = placed = true;
+            break;
+        }
+        if (prev == ckey) {
+            placed = true;
+            break;
+        }
+        h = (h + 1) & mask;
+    }
+    if (!placed) {
+        atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+        return;
+    }
+    double sx = sums[4 * j], sy = sums[4 * j + 1], sz = sums[4 * j + 2], n = sums[4 * j + 3];
+    const size_t pos = h;
+    if (!fresh) {
+        sx = dadd(acc[4 * pos], sx);
+        sy = dadd(acc[4 * pos + 1], sy);
+        sz = dadd(acc[4 * pos + 2], sz);
+        n = acc[4 * pos + 3] + n;
+    }
+    acc[4 * pos] = sx; acc[4 * pos + 1] = sy; acc[4 * pos + 2] = sz; acc[4 * pos + 3] = n;
+    vox[h].x = (float)ddiv(sx, n);
+    vox[h].y = (float)ddiv(sy, n);
+    vox[h].z = (float)ddiv(sz, n);
+    vox[h].n = (unsigned)n;
+}
+
+__global__ void __launch_bounds__(kBlock)
+vox_export_collect_kernel(const VoxEntry* __restrict__ vox, unsigned capacity,
+                          unsigned long long* __restrict__ out_keys, unsigned* __restrict__ out_pos,
+                          SortCtl* __restrict__ ctl, long long max_out) {
+    const unsigned h = blockIdx.x * kBlock + threadIdx.x;
+    if (h >= capacity) return;
+    const unsigned long long k = vox[h].key;
+    if (k == kEmptyKey || vox[h].n == 0) return;
+    const int base = atomicAdd(&ctl->n, 1);
+    if (base >= max_out) return;
+    out_keys[base] = k;  // map_cell_key of a 1-voxel cell == the packed voxel key
+    out_pos[base] = h;
+}
+
+__global__ void __launch_bounds__(kBlock)
+vox_export_write_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
+                        const unsigned* __restrict__ valsA, const unsigned* __restrict__ valsB,
+                        const SortCtl* __restrict__ ctl, const VoxEntry* __restrict__ vox,
+                        float4* __restrict__ out_pts, int* __restrict__ out_keys) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= ctl->n) return;
+    const bool odd = ctl->npasses & 1;
+    const unsigned long long k = (odd ? keysB : keysA)[i];
+    const VoxEntry e = vox[(odd ? valsB : valsA)[i]];
+    out_pts[i] = make_float4(e.x, e.y, e.z, __int_as_float((int)e.n));
+    if (out_keys) {
+        out_keys[3 * i] = (int)((k >> 42) & 0x1FFFFF) - (1 << 20);
+        out_keys[3 * i + 1] = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
+        out_keys[3 * i + 2] = (int)(k & 0x1FFFFF) - (1 << 20);
+    }
 }
 
 // Compaction of the occupied voxels: packed 63-bit key (for the canonical sort) + slab position.
@@ -210,7 +308,7 @@ __global__ void gather_pos_kernel(const unsigned long long* keysA, const unsigne
 void map_free(Context* c) {
     MapState* m = c->map;
     if (!m) return;
-    cudaFree(m->entries); cudaFree(m->lut); cudaFree(m->lid); cudaFree(m->cent); cudaFree(m->acc);
+    cudaFree(m->entries); cudaFree(m->vox); cudaFree(m->lut); cudaFree(m->lid); cudaFree(m->cent); cudaFree(m->acc);
     cudaFree(m->counters); cudaFree(m->meta); cudaFree(m->pose); cudaFree(m->result);
     delete m;
     c->map = nullptr;
@@ -219,10 +317,14 @@ void map_free(Context* c) {
 int map_reset(Context* c) {
     MapState* m = c->map;
     if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
-    map_clear_kernel<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->entries, m->capacity, m->cap_slots);
-    B2_LAUNCH_CHECK(c);
-    if (m->brick > 1)
+    if (m->brick == 1) {
+        vox_clear_kernel<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->vox, m->capacity);
+        B2_LAUNCH_CHECK(c);
+    } else {
+        map_clear_kernel<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->entries, m->capacity, m->cap_slots);
+        B2_LAUNCH_CHECK(c);
         B2_CUDA_OK(c, cudaMemsetAsync(m->lut, 0, (size_t)m->capacity * m->lut_stride, c->stream));
+    }
     map_set_meta_kernel<<<1, 1, 0, c->stream>>>(m->meta, m->origin[0], m->origin[1], m->origin[2], m->voxel,
                                                 m->brick, m->pose, m->counters);
     B2_LAUNCH_CHECK(c);
@@ -237,6 +339,7 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
     if (brick < 1) brick = 1;
     if (brick > 6) return set_error(c, B2_ERR_INVALID, "map_init: max_corr/voxel = %g > 6 is not supported", max_corr / voxel);
     map_free(c);
+    c->ws_generation++;  // invalidates any captured graph that baked the old table addresses
     unsigned long long cap = 1024;
     while (cap < (unsigned long long)capacity_cells) cap <<= 1;
     const int cap_slots = brick * brick * brick;
@@ -248,10 +351,14 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
     m->lut_stride = (cap_slots + 15) / 16 * 16;
     m->capacity = (unsigned)cap;
     for (int d = 0; d < 3; ++d) m->origin[d] = origin[d];
-    B2_CUDA_OK(c, cudaMalloc(&m->entries, sizeof(CellEntry) * cap));
-    B2_CUDA_OK(c, cudaMalloc(&m->lut, (size_t)cap * m->lut_stride));
-    B2_CUDA_OK(c, cudaMalloc(&m->lid, (size_t)cap * cap_slots));
-    B2_CUDA_OK(c, cudaMalloc(&m->cent, sizeof(float4) * cap * cap_slots));
+    if (brick == 1) {
+        B2_CUDA_OK(c, cudaMalloc(&m->vox, sizeof(VoxEntry) * cap));
+    } else {
+        B2_CUDA_OK(c, cudaMalloc(&m->entries, sizeof(CellEntry) * cap));
+        B2_CUDA_OK(c, cudaMalloc(&m->lut, (size_t)cap * m->lut_stride));
+        B2_CUDA_OK(c, cudaMalloc(&m->lid, (size_t)cap * cap_slots));
+        B2_CUDA_OK(c, cudaMalloc(&m->cent, sizeof(float4) * cap * cap_slots));
+    }
     B2_CUDA_OK(c, cudaMalloc(&m->acc, sizeof(double) * 4 * cap * cap_slots));
     B2_CUDA_OK(c, cudaMalloc(&m->counters, sizeof(long long) * 2));
     B2_CUDA_OK(c, cudaMalloc(&m->meta, sizeof(GridMeta)));
@@ -267,7 +374,8 @@ int map_grid_view(Context* c, GridView* g) {
     g->mask = m->capacity - 1;
     g->pts = m->cent;
     g->meta = m->meta;
-    g->is_map = 1;
+    g->is_map = m->brick == 1 ? 2 : 1;
+    g->vox = m->vox;
     return B2_OK;
 }
 
@@ -289,10 +397,15 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
     VoxelSortOut vs;
     B2_TRY(voxel_downsample(c, pts, n_max, n_dev, nullptr, 1, m->voxel, /*origin_mode=*/1, m->origin, T_dev, out, &vs));
     const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
-    map_merge_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(dkeys, dsums, vs.ctl, m->entries,
-                                                                     m->capacity - 1, m->lut, m->lid, m->cent, m->acc,
-                                                                     m->counters, m->brick, m->cap_slots,
-                                                                     m->lut_stride, max_cells, c->dev_status);
+    if (m->brick == 1)
+        vox_merge_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(dkeys, dsums, vs.ctl, m->vox, m->capacity - 1,
+                                                                         m->acc, m->counters, max_cells,
+                                                                         c->dev_status);
+    else
+        map_merge_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(dkeys, dsums, vs.ctl, m->entries,
+                                                                         m->capacity - 1, m->lut, m->lid, m->cent,
+                                                                         m->acc, m->counters, m->brick, m->cap_slots,
+                                                                         m->lut_stride, max_cells, c->dev_status);
     B2_LAUNCH_CHECK(c);
     m->host_voxels_bound += n_max;
     return B2_OK;
@@ -325,16 +438,24 @@ int map_export(Context* c, float4* out_pts, int* out_keys, long long max_out, lo
     B2_WS(c, pos, unsigned, WS_EXPORT_KEYS, sizeof(unsigned) * (size_t)n);
     B2_WS(c, ctl, SortCtl, WS_CTL, sizeof(SortCtl));
     B2_CUDA_OK(c, cudaMemsetAsync(ctl, 0, sizeof(SortCtl), c->stream));
-    map_export_collect_kernel<<<div_up(m->capacity, kBlock), kBlock, 0, c->stream>>>(
-        m->entries, m->capacity, m->lid, m->brick, m->cap_slots, keysA, pos, ctl, (long long)n);
+    if (m->brick == 1)
+        vox_export_collect_kernel<<<div_up(m->capacity, kBlock), kBlock, 0, c->stream>>>(m->vox, m->capacity, keysA,
+                                                                                        pos, ctl, (long long)n);
+    else
+        map_export_collect_kernel<<<div_up(m->capacity, kBlock), kBlock, 0, c->stream>>>(
+            m->entries, m->capacity, m->lid, m->brick, m->cap_slots, keysA, pos, ctl, (long long)n);
     B2_LAUNCH_CHECK(c);
     map_export_ctl_kernel<<<1, 1, 0, c->stream>>>(ctl, (long long)n);
     B2_LAUNCH_CHECK(c);
     B2_TRY(radix_sort_pairs(c, keysA, keysB, valsA, valsB, ctl, n, 8));
     gather_pos_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(keysA, keysB, valsA, valsB, pos, ctl);
     B2_LAUNCH_CHECK(c);
-    map_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->cent,
-                                                                        m->acc, out_pts, out_keys);
+    if (m->brick == 1)
+        vox_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->vox,
+                                                                            out_pts, out_keys);
+    else
+        map_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->cent,
+                                                                            m->acc, out_pts, out_keys);
     B2_LAUNCH_CHECK(c);
     B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return B2_OK;

@@ -66,6 +66,17 @@ def make_corridor_scene(seed: int = 0, length: float = 60.0, width: float = 3.0,
         w[2] = rng.uniform(0.3, height)
         y0 = width - w[1]
         boxes.append([x0, y0, 0.0, x0 + w[0], width, w[2]])
+    # pilasters on the viewed wall and low clutter on the floor: without them a corridor leaves the
+    # along-axis translation unobservable and point-to-point ICP slides (the classic degeneracy)
+    x = 0.3
+    while x < length - 0.5:
+        d = rng.uniform(0.06, 0.16)
+        boxes.append([x, width - d, 0.0, x + rng.uniform(0.08, 0.2), width, height])
+        if rng.random() < 0.6:
+            s = rng.uniform(0.15, 0.4, size=3)
+            yc = rng.uniform(1.6, width - 0.5)
+            boxes.append([x + 0.3, yc, 0.0, x + 0.3 + s[0], yc + s[1], s[2]])
+        x += rng.uniform(0.45, 0.9)
     return Scene(size=(length, width, height), boxes=np.asarray(boxes, dtype=np.float64).reshape(-1, 6))
 
 
