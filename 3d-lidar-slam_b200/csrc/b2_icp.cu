@@ -28,7 +28,8 @@ namespace b2 {
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kThreads = 640;   // 20 warps, one CTA per SM (<= 96 registers per thread)
+constexpr int kCtasPerSm = 1;
 constexpr int kWarps = kThreads / 32;
 constexpr int kTerms = 32;
 constexpr unsigned kFull = 0xffffffffu;
@@ -222,23 +223,23 @@ __device__ __forceinline__ bool polar_rotation(double a, double b, double c, dou
 // small matrix stays in registers (a single GPU thread retires roughly one dependent instruction
 // per 6-10 cycles, so the instruction count of this tail is what the iteration latency is made of).
 template <int MODE>
-__device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams prm, IcpState* st, IcpResultDev* res,
-                                      int* ndone) {
+__device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams prm, const IcpState& cur,
+                                      IcpState* st, IcpResultDev* res, int* ndone) {
     const double n = MODE == 0 ? S[16] : S[28];
     const double sd2 = MODE == 0 ? S[15] : S[27];
     const double fitness = ns > 0 ? n / (double)ns : 0.0;
     const double rmse = n > 0 ? sqrt(sd2 / n) : 0.0;
     bool done = false;
-    if (st->has_prev && fabs(st->prev_fitness - fitness) < prm.rel_fitness &&
-        fabs(st->prev_rmse - rmse) < prm.rel_rmse)
+    if (cur.has_prev && fabs(cur.prev_fitness - fitness) < prm.rel_fitness &&
+        fabs(cur.prev_rmse - rmse) < prm.rel_rmse)
         done = true;
-    if (st->iter >= prm.max_iter) done = true;
+    if (cur.iter >= prm.max_iter) done = true;
     st->fitness = fitness;
     st->rmse = rmse;
     st->n_corr = (int)n;
     double T[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) T[k] = st->T[k];
+    for (int k = 0; k < 12; ++k) T[k] = cur.T[k];
     if (done) {
         st->done = 1;
 #pragma unroll
@@ -246,7 +247,7 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
         res->T[12] = 0.0; res->T[13] = 0.0; res->T[14] = 0.0; res->T[15] = 1.0;
         res->fitness = fitness;
         res->rmse = rmse;
-        res->iterations = st->iter;
+        res->iterations = cur.iter;
         res->n_corr = (int)n;
         atomicAdd(ndone, 1);
         return;
@@ -263,7 +264,7 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
             C[6] = S[12] * inv - mq2 * mp0; C[7] = S[13] * inv - mq2 * mp1; C[8] = S[14] * inv - mq2 * mp2;
             if (!polar_rotation(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], R))
                 rotation_from_covariance(C, R);
-            const double p0 = st->pivot[0], p1 = st->pivot[1], p2 = st->pivot[2];
+            const double p0 = cur.pivot[0], p1 = cur.pivot[1], p2 = cur.pivot[2];
             mp0 += p0; mp1 += p1; mp2 += p2;
             mq0 += p0; mq1 += p1; mq2 += p2;
             U[0] = R[0]; U[1] = R[1]; U[2] = R[2];  U[3] = mq0 - (R[0] * mp0 + R[1] * mp1 + R[2] * mp2);
@@ -291,7 +292,7 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
         st->T[4 * r + 2] = u0 * T[2] + u1 * T[6] + u2 * T[10];
         st->T[4 * r + 3] = u0 * T[3] + u1 * T[7] + u2 * T[11] + u3;
     }
-    st->iter += 1;
+    st->iter = cur.iter + 1;
     st->prev_fitness = fitness;
     st->prev_rmse = rmse;
     st->has_prev = 1;
@@ -300,10 +301,11 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
 // ---------------------------------------------------------------------------
 // the hot kernels
 // ---------------------------------------------------------------------------
-// Work decomposition: a warp serves FOUR queries at a time, eight lanes each.  Lane g of a group
-// probes stencil cells {g, g+8, g+16, g+24 (<27)}: the four hash probes of a lane are issued back to
-// back (memory-level parallelism 4 per lane, 128 per warp) before any of them is consumed, and the
-// group's arg-min is a 3-step shuffle butterfly.  The group leader (lane g == 0) owns the query:
+// Work decomposition: a warp serves EIGHT queries at a time, four lanes each, so that a 21.7k-point
+// source is one round over the 148 x 160 groups of the grid (one 640-thread CTA per SM).  Lane g of a
+// group probes stencil cells {g, g+4, ..., g+24 (<27)} in batches of four hash probes that are issued
+// back to back (memory-level parallelism 4 per lane, 128 per warp) before any of them is consumed,
+// and the group's arg-min is a 2-step shuffle butterfly.  The group leader (lane g == 0) owns the query:
 // it loads and transforms the point, and adds the query's contribution to its private column of
 // the shared-memory accumulators, so no per-query warp-wide reduction is needed.
 //
@@ -327,7 +329,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 #define B2_TS(slot) do {} while (0)
 #define B2_TS_BLOCK(k) do {} while (0)
 #endif
-constexpr int kGroup = 8;
+constexpr int kGroup = 4;
+constexpr int kCellsPerLane = (27 + kGroup - 1) / kGroup;  // 7
+constexpr int kProbeBatch = 4;  // probes of a lane in flight together
 constexpr int kLeaders = kThreads / kGroup;  // accumulator columns per CTA
 
 struct SearchArgs {
@@ -380,80 +384,86 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
     int best_idx = 0x7fffffff;
     float bx = 0.f, by = 0.f, bz = 0.f;
     if (valid) {
-        unsigned long long key[4];
-        unsigned hpos[4];
-        bool live[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int c = g + kGroup * k;
-            const int nx = cx + c / 9 - 1, ny = cy + (c / 3) % 3 - 1, nz = cz + c % 3 - 1;
-            if (KIND) {
-                live[k] = c < 27 && nx > -(1 << 20) && nx < (1 << 20) && ny > -(1 << 20) && ny < (1 << 20) &&
-                          nz > -(1 << 20) && nz < (1 << 20);
-                key[k] = map_cell_key(nx, ny, nz);
-            } else {
-                live[k] = c < 27 && nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
-                key[k] = pair_cell_key(a.pair, nx, ny, nz);
-            }
-            hpos[k] = cell_hash(key[k]) & a.mask;
-        }
-        if (KIND == 2) {
-            unsigned long long ek[4], exy[4], ezn[4], epad[4];
+        for (int k0 = 0; k0 < kCellsPerLane; k0 += kProbeBatch) {
+            unsigned long long key[kProbeBatch];
+            unsigned hpos[kProbeBatch];
+            bool live[kProbeBatch];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (live[k]) ldg256(a.vox + hpos[k], ek[k], exy[k], ezn[k], epad[k]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!live[k]) continue;
-                unsigned h = hpos[k];
-                while (ek[k] != key[k] && ek[k] != kEmptyKey) {  // collision chain (rare at load <= 0.5)
-                    h = (h + 1) & a.mask;
-                    ldg256(a.vox + h, ek[k], exy[k], ezn[k], epad[k]);
+            for (int k = 0; k < kProbeBatch; ++k) {
+                const int c = g + kGroup * (k0 + k);
+                const int c3 = (c * 171) >> 9;  // c / 3 for c < 128
+                const int c9 = (c * 57) >> 9;   // c / 9
+                const int nx = cx + c9 - 1, ny = cy + (c3 - 3 * c9) - 1, nz = cz + (c - 3 * c3) - 1;
+                const bool in_stencil = (k0 + k) < kCellsPerLane && c < 27;
+                if (KIND) {
+                    live[k] = in_stencil && nx > -(1 << 20) && nx < (1 << 20) && ny > -(1 << 20) && ny < (1 << 20) &&
+                              nz > -(1 << 20) && nz < (1 << 20);
+                    key[k] = map_cell_key(nx, ny, nz);
+                } else {
+                    live[k] = in_stencil && nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
+                    key[k] = pair_cell_key(a.pair, nx, ny, nz);
                 }
-                if (ek[k] == key[k] && (unsigned)(ezn[k] >> 32) != 0u) {
-                    const float x = __uint_as_float((unsigned)exy[k]);
-                    const float y = __uint_as_float((unsigned)(exy[k] >> 32));
-                    const float z = __uint_as_float((unsigned)ezn[k]);
-                    const double d2 = dist2_strict(Px, Py, Pz, (double)x, (double)y, (double)z);
-                    if (d2 < best || (d2 == best && (int)h < best_idx)) {
-                        best = d2;
-                        best_idx = (int)h;
-                        bx = x; by = y; bz = z;
+                hpos[k] = cell_hash(key[k]) & a.mask;
+            }
+            if (KIND == 2) {
+                unsigned long long ek[kProbeBatch], exy[kProbeBatch], ezn[kProbeBatch], epad[kProbeBatch];
+#pragma unroll
+                for (int k = 0; k < kProbeBatch; ++k)
+                    if (live[k]) ldg256(a.vox + hpos[k], ek[k], exy[k], ezn[k], epad[k]);
+#pragma unroll
+                for (int k = 0; k < kProbeBatch; ++k) {
+                    if (!live[k]) continue;
+                    unsigned h = hpos[k];
+                    while (ek[k] != key[k] && ek[k] != kEmptyKey) {  // collision chain (rare at load <= 0.5)
+                        h = (h + 1) & a.mask;
+                        ldg256(a.vox + h, ek[k], exy[k], ezn[k], epad[k]);
+                    }
+                    if (ek[k] == key[k] && (unsigned)(ezn[k] >> 32) != 0u) {
+                        const float x = __uint_as_float((unsigned)exy[k]);
+                        const float y = __uint_as_float((unsigned)(exy[k] >> 32));
+                        const float z = __uint_as_float((unsigned)ezn[k]);
+                        const double d2 = dist2_strict(Px, Py, Pz, (double)x, (double)y, (double)z);
+                        if (d2 < best || (d2 == best && (int)h < best_idx)) {
+                            best = d2;
+                            best_idx = (int)h;
+                            bx = x; by = y; bz = z;
+                        }
                     }
                 }
-            }
-        } else {
-            uint4 raw[4];
+            } else {
+                uint4 raw[kProbeBatch];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (live[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(a.entries + hpos[k]));
+                for (int k = 0; k < kProbeBatch; ++k)
+                    if (live[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(a.entries + hpos[k]));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!live[k]) continue;
-                unsigned h = hpos[k];
-                unsigned long long kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
-                while (kk != key[k] && kk != kEmptyKey) {
-                    h = (h + 1) & a.mask;
-                    raw[k] = __ldg(reinterpret_cast<const uint4*>(a.entries + h));
-                    kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
-                }
-                if (kk != key[k]) continue;
-                const unsigned off = raw[k].z;
-                const int cnt = (int)raw[k].w;
-                for (int j = 0; j < cnt; ++j) {
-                    const float4 t = __ldg(a.gpts + off + j);
-                    const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                    const int idx = __float_as_int(t.w);
-                    if (d2 < best || (d2 == best && idx < best_idx)) {
-                        best = d2;
-                        best_idx = idx;
-                        bx = t.x; by = t.y; bz = t.z;
+                for (int k = 0; k < kProbeBatch; ++k) {
+                    if (!live[k]) continue;
+                    unsigned h = hpos[k];
+                    unsigned long long kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
+                    while (kk != key[k] && kk != kEmptyKey) {
+                        h = (h + 1) & a.mask;
+                        raw[k] = __ldg(reinterpret_cast<const uint4*>(a.entries + h));
+                        kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
+                    }
+                    if (kk != key[k]) continue;
+                    const unsigned off = raw[k].z;
+                    const int cnt = (int)raw[k].w;
+                    for (int j = 0; j < cnt; ++j) {
+                        const float4 t = __ldg(a.gpts + off + j);
+                        const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
+                        const int idx = __float_as_int(t.w);
+                        if (d2 < best || (d2 == best && idx < best_idx)) {
+                            best = d2;
+                            best_idx = idx;
+                            bx = t.x; by = t.y; bz = t.z;
+                        }
                     }
                 }
             }
         }
     }
-    // ---- arg-min over the 8 lanes of the group: (d2, idx) lexicographic -----------------------------
+    // ---- arg-min over the lanes of the group: (d2, idx) lexicographic -----------------------------
     double gbest = best;
     int gidx = best_idx;
 #pragma unroll
@@ -467,7 +477,7 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
     }
     const bool found = valid && gbest < a.r2;
     const unsigned winners = __ballot_sync(kFull, found && best == gbest && best_idx == gidx);
-    const int wl = lead + __ffs((winners >> lead) & 0xffu) - 1;  // meaningful only when found
+    const int wl = lead + __ffs((winners >> lead) & ((1u << kGroup) - 1u)) - 1;  // meaningful only when found
     const float Qxf = __shfl_sync(kFull, bx, wl & 31);
     const float Qyf = __shfl_sync(kFull, by, wl & 31);
     const float Qzf = __shfl_sync(kFull, bz, wl & 31);
@@ -527,11 +537,11 @@ template <int NT>
 __device__ __forceinline__ void grid_fold(const double* __restrict__ partial, int n_cta, double (*sRed)[kTerms],
                                           double* __restrict__ sSum) {
     constexpr int kParts = kThreads / 32;
-    constexpr int kMaxPer = (2 * kSMs + kParts - 1) / kParts;
+    constexpr int kMaxPer = (kCtasPerSm * kSMs + kParts - 1) / kParts;
     const int j = threadIdx.x & 31, part = threadIdx.x >> 5;
     double s = 0.0;
     if (j < NT) {
-        if (n_cta <= 2 * kSMs) {
+        if (n_cta <= kCtasPerSm * kSMs) {
             double v[kMaxPer];
 #pragma unroll
             for (int k = 0; k < kMaxPer; ++k) {
@@ -556,7 +566,7 @@ __device__ __forceinline__ void grid_fold(const double* __restrict__ partial, in
 }
 
 template <int MODE, int KIND>  // KIND 0: pair grid, 1: resident map with slabs, 2: dense resident map
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs, const int* __restrict__ ns_dev,
                 int ns_max, const CellEntry* __restrict__ entries, unsigned mask,
                 const float4* __restrict__ gpts, const VoxEntry* __restrict__ vox,
@@ -568,21 +578,22 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     constexpr int NT = MODE == 0 ? 17 : 29;  // live accumulator terms
     const int pair = blockIdx.y;
     IcpState* st = states + pair;
-    if (st->done) return;
 
-    __shared__ double sT[12];
-    __shared__ double sPivot[3];
+    __shared__ IcpState sState;  // snapshot of the pair's state: every later read is on-chip
     __shared__ GridMeta sMeta;
     __shared__ double sAccL[NT][kLeaders];
     __shared__ double sRed[kThreads / 32][kTerms];
     __shared__ double sSum[kTerms];
     __shared__ int sLast;
+    static_assert(sizeof(IcpState) % 8 == 0 && sizeof(GridMeta) % 8 == 0, "copied as 8-byte words");
 
     B2_TS_BLOCK(0);
-    if (threadIdx.x < 12) sT[threadIdx.x] = st->T[threadIdx.x];
-    if (threadIdx.x < 3) sPivot[threadIdx.x] = st->pivot[threadIdx.x];
-    if (threadIdx.x == 0) sMeta = metas[KIND ? 0 : pair];
-    for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
+    // all prologue loads are independent of each other: one memory round trip, not a chain
+    if (threadIdx.x < sizeof(IcpState) / 8)
+        reinterpret_cast<double*>(&sState)[threadIdx.x] = reinterpret_cast<const double*>(st)[threadIdx.x];
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(GridMeta) / 8)
+        reinterpret_cast<double*>(&sMeta)[threadIdx.x - 32] =
+            reinterpret_cast<const double*>(metas + (KIND ? 0 : pair))[threadIdx.x - 32];
     int sb, se;
     if (src_offs) {
         sb = src_offs[pair];
@@ -591,7 +602,11 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
         sb = 0;
         se = ns_dev ? min(*ns_dev, ns_max) : ns_max;
     }
+    for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
     __syncthreads();
+    if (sState.done) return;
+    const double* sT = sState.T;
+    const double* sPivot = sState.pivot;
 
     SearchArgs a;
     a.entries = entries; a.vox = vox; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
@@ -604,9 +619,9 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     const int col = threadIdx.x / kGroup;
     // queries are dealt to groups round-robin over (round, CTA, group) so every CTA gets the same load
     const int groups_total = gridDim.x * kLeaders;
-    const int warp_first = blockIdx.x * kLeaders + col - (lane >> 3);
+    const int warp_first = blockIdx.x * kLeaders + col - lane / kGroup;
     for (int q0 = sb + warp_first; q0 < se; q0 += groups_total) {  // warp-uniform trip count
-        const int q = q0 + (lane >> 3);
+        const int q = q0 + lane / kGroup;
         const bool valid = q < se;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if ((lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
@@ -632,7 +647,7 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     B2_TS(1);
     if (threadIdx.x == 0) {
         tickets[pair] = 0;
-        icp_step<MODE>(sSum, se - sb, prm, st, results + pair, ndone);
+        icp_step<MODE>(sSum, se - sb, prm, sState, st, results + pair, ndone);
     }
     B2_TS(2);
 }
@@ -655,7 +670,7 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 constexpr int kPersistRounds = 2;  // query points a group keeps in registers across steps
 
 template <int MODE, int KIND>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
                    const CellEntry* __restrict__ entries, unsigned mask, const float4* __restrict__ gpts,
                    const VoxEntry* __restrict__ vox, const GridMeta* __restrict__ metas,
@@ -687,12 +702,12 @@ icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_de
     const int col = threadIdx.x / kGroup;
     const bool leader = (lane & (kGroup - 1)) == 0;
     const int groups_total = gridDim.x * kLeaders;
-    const int warp_first = blockIdx.x * kLeaders + col - (lane >> 3);
+    const int warp_first = blockIdx.x * kLeaders + col - lane / kGroup;
     // the queries of a group do not change between steps: keep the first rounds in registers
     float4 pq[kPersistRounds];
 #pragma unroll
     for (int r = 0; r < kPersistRounds; ++r) {
-        const int q = warp_first + r * groups_total + (lane >> 3);
+        const int q = warp_first + r * groups_total + lane / kGroup;
         pq[r] = (leader && q < se) ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const unsigned n_cta = gridDim.x;
@@ -710,12 +725,12 @@ icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_de
         for (int r = 0; r < kPersistRounds; ++r) {
             const int q0 = warp_first + r * groups_total;
             if (q0 < se) {
-                const int q = q0 + (lane >> 3);
+                const int q = q0 + lane / kGroup;
                 search_round<MODE, KIND>(a, sT, sPivot, sMeta, pq[r], q < se, q, sAccL, col);
             }
         }
         for (int q0 = warp_first + kPersistRounds * groups_total; q0 < se; q0 += groups_total) {
-            const int q = q0 + (lane >> 3);
+            const int q = q0 + lane / kGroup;
             const bool valid = q < se;
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if (leader && valid) p = __ldg(src + q);
@@ -738,7 +753,15 @@ icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_de
             grid_fold<NT>(partial, (int)n_cta, sRed, sSum);
             B2_PTS(4);
             if (threadIdx.x == 0) {
-                icp_step<MODE>(sSum, se, prm, st, results, ndone);
+                {
+                    IcpState cur;
+                    for (int k = 0; k < 16; ++k) cur.T[k] = st->T[k];
+                    cur.fitness = st->fitness; cur.rmse = st->rmse;
+                    cur.prev_fitness = st->prev_fitness; cur.prev_rmse = st->prev_rmse;
+                    for (int k = 0; k < 3; ++k) cur.pivot[k] = st->pivot[k];
+                    cur.iter = st->iter; cur.done = st->done; cur.n_corr = st->n_corr; cur.has_prev = st->has_prev;
+                    icp_step<MODE>(sSum, se, prm, cur, st, results, ndone);
+                }
                 B2_PTS(5);
                 __threadfence();
                 st_release_u32(&sync->epoch, step + 1);
@@ -845,7 +868,7 @@ int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max,
     }
     int grid = div_up(ns_max, kLeaders);  // one query per 8-lane group when it fits
     if (grid > max_ctas) grid = max_ctas;
-    if (grid > 2 * kSMs) grid = 2 * kSMs;
+    if (grid > kCtasPerSm * kSMs) grid = kCtasPerSm * kSMs;
     if (grid < 1) grid = 1;
     const CellEntry* entries = g.entries;
     unsigned mask = g.mask;
@@ -873,11 +896,13 @@ int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev
 }
 
 int icp_grid_x(int ns_max, int n_pairs) {
-    // one CTA of 16 warps per ~64 queries, capped at two resident CTAs per SM for a
-    // single pair; batches already fill the machine through gridDim.y
-    int gx = div_up(ns_max / (n_pairs > 0 ? n_pairs : 1) + 1, kWarps * 4);
-    int cap = n_pairs >= 2 * kSMs ? 2 : (2 * kSMs) / (n_pairs > 0 ? n_pairs : 1);
-    if (cap < 1) cap = 1;
+    // single pair: one query per 4-lane group when it fits (160 groups per CTA, one CTA per SM);
+    // batches fill the machine through gridDim.y and use few CTAs per pair
+    const int pairs = n_pairs > 0 ? n_pairs : 1;
+    int gx = div_up(ns_max / pairs + 1, kLeaders);
+    int cap = (kCtasPerSm * kSMs) / pairs;
+    if (cap < 2) cap = 2;
+    if (pairs == 1) cap = kCtasPerSm * kSMs;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     return gx;
@@ -893,7 +918,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     if (!(prm.max_corr > 0.0)) return set_error(c, B2_ERR_INVALID, "max_correspondence_distance must be > 0");
     const int gx = icp_grid_x(ns_max, n_pairs);
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
-    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > 2 * kSMs ? gx : 2 * kSMs) * n_pairs);
+    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs);
     B2_WS(c, tickets, int, WS_ICP_TICKET, sizeof(int) * ((size_t)n_pairs + 1));
     int* ndone = tickets + n_pairs;
     icp_init_kernel<<<div_up(n_pairs, 128), 128, 0, c->stream>>>(src, src_offsets, ns_dev, ns_max, init_dev, 16,
