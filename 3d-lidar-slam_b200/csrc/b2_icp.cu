@@ -588,12 +588,28 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     static_assert(sizeof(IcpState) % 8 == 0 && sizeof(GridMeta) % 8 == 0, "copied as 8-byte words");
 
     B2_TS_BLOCK(0);
-    // all prologue loads are independent of each other: one memory round trip, not a chain
-    if (threadIdx.x < sizeof(IcpState) / 8)
-        reinterpret_cast<double*>(&sState)[threadIdx.x] = reinterpret_cast<const double*>(st)[threadIdx.x];
-    else if (threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(GridMeta) / 8)
+    // Programmatic dependent launch: let the next step's grid be scheduled as soon as our CTAs retire
+    // (all but the solving CTA leave right after the search), and do everything that does not depend
+    // on the previous step — grid metadata, accumulator reset, this group's query point — before
+    // waiting for the previous grid's writes (the pair state) to land.
+    asm volatile("griddepcontrol.launch_dependents;");
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(GridMeta) / 8)
         reinterpret_cast<double*>(&sMeta)[threadIdx.x - 32] =
             reinterpret_cast<const double*>(metas + (KIND ? 0 : pair))[threadIdx.x - 32];
+    for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
+    const int lane = threadIdx.x & 31;
+    const int col = threadIdx.x / kGroup;
+    const int groups_total = gridDim.x * kLeaders;
+    const int warp_first = blockIdx.x * kLeaders + col - lane / kGroup;
+    float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!src_offs) {  // single pair: prefetch the first query (the buffer holds ns_max rows; validity is decided later)
+        const int q = warp_first + lane / kGroup;
+        if ((lane & (kGroup - 1)) == 0 && q < ns_max) p_first = __ldg(src + q);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // all remaining prologue loads are independent of each other: one memory round trip, not a chain
+    if (threadIdx.x < sizeof(IcpState) / 8)
+        reinterpret_cast<double*>(&sState)[threadIdx.x] = reinterpret_cast<const double*>(st)[threadIdx.x];
     int sb, se;
     if (src_offs) {
         sb = src_offs[pair];
@@ -602,7 +618,6 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
         sb = 0;
         se = ns_dev ? min(*ns_dev, ns_max) : ns_max;
     }
-    for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
     __syncthreads();
     if (sState.done) return;
     const double* sT = sState.T;
@@ -615,16 +630,14 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     a.r2 = dmul(prm.max_corr, prm.max_corr);
     a.corr_out = corr_out; a.d2_out = d2_out; a.search_only = search_only;
 
-    const int lane = threadIdx.x & 31;
-    const int col = threadIdx.x / kGroup;
-    // queries are dealt to groups round-robin over (round, CTA, group) so every CTA gets the same load
-    const int groups_total = gridDim.x * kLeaders;
-    const int warp_first = blockIdx.x * kLeaders + col - lane / kGroup;
+    // queries are dealt to groups round-robin over (round, CTA, group)
+    bool first = !src_offs;
     for (int q0 = sb + warp_first; q0 < se; q0 += groups_total) {  // warp-uniform trip count
         const int q = q0 + lane / kGroup;
         const bool valid = q < se;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
+        float4 p = p_first;
+        if (!first && (lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
+        first = false;
         search_round<MODE, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
     }
     if (search_only) return;
@@ -812,9 +825,21 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                  const GridView& g, const float4* nrm, const int* tgt_offs, const IcpParams& prm, IcpState* st,
                  double* partial, int* tickets, IcpResultDev* res, int* corr, int* ndone, double* d2_out,
                  int search_only) {
-    icp_iter_kernel<MODE, IS_MAP><<<grid, kThreads, 0, c->stream>>>(src, src_offs, ns_dev, ns_max, g.entries, g.mask,
-                                                                   g.pts, g.vox, g.meta, nrm, tgt_offs, prm, st, partial,
-                                                                   tickets, res, corr, ndone, d2_out, search_only);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("B2_NO_PDL") != nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, icp_iter_kernel<MODE, IS_MAP>, src, src_offs, ns_dev, ns_max,
+                       (const CellEntry*)g.entries, g.mask, (const float4*)g.pts, (const VoxEntry*)g.vox,
+                       (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets, res, corr, ndone, d2_out,
+                       search_only);
 }
 
 // Candidate census of the resident-map stencil (the data-dependent term of the byte model).
@@ -1009,6 +1034,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
                 if (h[8 + 2 * b + 1] < tmain_min) tmain_min = h[8 + 2 * b + 1];
                 if (h[8 + 2 * b + 1] > tmain_max) tmain_max = h[8 + 2 * b + 1];
             }
+            fprintf(stderr, "[b2 blocks main-done-minus-start ns]");
+            for (int b = 0; b < gx && b < 1024; ++b) fprintf(stderr, " %llu", h[8 + 2 * b + 1] - h[8 + 2 * b]);
+            fprintf(stderr, "\n");
             fprintf(stderr, "[b2 tail] last launch (ns from first CTA start): last CTA start %llu | main done min %llu max %llu | "
                             "last-CTA: ticket won %llu, reduced %llu, step done %llu\n",
                     tstart_max - t0, tmain_min - t0, tmain_max - t0, h[0] - t0, h[1] - t0, h[2] - t0);

@@ -41,7 +41,10 @@ DS_VOXEL = 0.02
 MAX_CORR = 0.05
 MAX_ITER = 30
 MAP_ORIGIN = (-50.0, -50.0, -50.0)
-CORRIDOR_LEN = 210.0          # ~2.0 M voxels at 5 cm
+CORRIDOR_LEN = 210.0          # ~2.1 M voxels at 5 cm
+# hash slots of the resident map: load factor 0.06 keeps linear-probe chains (which a warp pays as the
+# maximum over its 32 lanes) short; 32 B entry + 32 B accumulator per slot = 2 GiB of the 180 GB HBM
+MAP_CAPACITY = int(os.environ.get("B2_BENCH_CAP", 1 << 25))
 SCAN_POINTS = 49152
 METRIC = "scans/s ICP+fuse (49k-pt scan->2M-pt map)"
 
@@ -116,7 +119,7 @@ def preload_map(engine, scene, device):
     import torch
     from lidar_slam_b200 import synth
 
-    engine.map_init(MAP_VOXEL, MAP_ORIGIN, MAX_CORR, 1 << 23)
+    engine.map_init(MAP_VOXEL, MAP_ORIGIN, MAX_CORR, MAP_CAPACITY)
     for x0 in range(0, int(CORRIDOR_LEN), 10):
         pts = synth.sample_scene_surface(scene, 0.02, (float(x0), float(x0 + 10)), seed=x0, device=device)
         p4 = torch.zeros((pts.shape[0], 4), dtype=torch.float32, device=device)
@@ -246,7 +249,8 @@ def run_ours(args):
                    "max_corr_m": MAX_CORR, "max_iteration": MAX_ITER, "mean_icp_iterations": round(iters, 2),
                    "mean_fitness": round(fit, 4), "final_pose_error_m": round(err, 4),
                    "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                   "l2": "map tables 64+64+128 MB > 126 MB L2; scans replayed over a 1.3 m path between steps"},
+                   "map_hash_slots": MAP_CAPACITY,
+                   "l2": "map tables (1 GiB entries + 1 GiB accumulators) >> 126 MB L2; a scan touches ~4 MB of them"},
         "e2e": {"value": round(e2e_value, 2), "unit": "scans/s", "h2d_bytes_per_step": h2d_per_step,
                 "d2h_bytes_per_step": d2h_per_step},
         "gpu_launches": int(gpu_launches),
