@@ -92,7 +92,7 @@ sort_scan_kernel(unsigned* __restrict__ hist, int total, const SortCtl* __restri
 __global__ void __launch_bounds__(kThreads)
 sort_scatter_kernel(unsigned long long* keysA, unsigned long long* keysB, unsigned* valsA, unsigned* valsB,
                     const SortCtl* __restrict__ ctl, int pass, const unsigned* __restrict__ hist,
-                    int vals_implicit) {
+                    int vals_implicit, int fused_scan) {
     if (pass >= ctl->npasses) return;
     const bool odd = pass & 1;
     const unsigned long long* __restrict__ kin = odd ? keysB : keysA;
@@ -107,7 +107,33 @@ sort_scatter_kernel(unsigned long long* keysA, unsigned long long* keysB, unsign
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    running[threadIdx.x] = hist[threadIdx.x * gridDim.x + blockIdx.x];
+    if (!fused_scan) {
+        running[threadIdx.x] = hist[threadIdx.x * gridDim.x + blockIdx.x];  // already scanned
+    } else {
+        // small grids: every CTA derives its own bases from the raw histogram table (256 x gridDim.x
+        // counters) instead of paying a separate one-CTA scan launch per pass
+        unsigned below = 0, total = 0;
+        for (unsigned b = 0; b < gridDim.x; ++b) {
+            const unsigned v = hist[threadIdx.x * gridDim.x + b];
+            total += v;
+            if (b < blockIdx.x) below += v;
+        }
+        // exclusive scan of the 256 digit totals
+        unsigned incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) digit_base[w] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k)
+            if (k < w) woff += digit_base[k];
+        __syncthreads();
+        running[threadIdx.x] = woff + incl - total + below;
+    }
     int begin, end;
     const int n = ctl->n;
     block_range(n, begin, end);
@@ -176,12 +202,16 @@ int radix_sort_pairs(Context* c, unsigned long long* keysA, unsigned long long* 
     int nblocks = div_up(n_max, kChunk);
     if (nblocks > kMaxBlocks) nblocks = kMaxBlocks;
     B2_WS(c, hist, unsigned, WS_HIST, sizeof(unsigned) * 256 * (size_t)kMaxBlocks);
+    const int fused_scan = nblocks <= 64;
     for (int p = 0; p < max_passes; ++p) {
         sort_hist_kernel<<<nblocks, kThreads, 0, c->stream>>>(keysA, keysB, ctl, p, hist);
         B2_LAUNCH_CHECK(c);
-        sort_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, 256 * nblocks, ctl, p);
-        B2_LAUNCH_CHECK(c);
-        sort_scatter_kernel<<<nblocks, kThreads, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, p, hist, 1);
+        if (!fused_scan) {
+            sort_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, 256 * nblocks, ctl, p);
+            B2_LAUNCH_CHECK(c);
+        }
+        sort_scatter_kernel<<<nblocks, kThreads, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, p, hist, 1,
+                                                                  fused_scan);
         B2_LAUNCH_CHECK(c);
     }
     return B2_OK;
