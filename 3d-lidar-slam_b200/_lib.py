@@ -24,6 +24,7 @@ EXPORTS = [
     "b2_estimate_normals", "b2_nn_search", "b2_icp", "b2_transform", "b2_map_init", "b2_map_reset",
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
+    "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points",
 ]
 
 
@@ -86,6 +87,9 @@ def load():
         "b2_slam_scan": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan_dev": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_map_stencil_candidates": [vp, vp, i32, pd, C.POINTER(i64)],
+        "b2_radius_outlier_mask": [vp, vp, i32, i32, f64, vp, C.POINTER(i32)],
+        "b2_statistical_outlier_mask": [vp, vp, i32, i32, f64, f64, vp, C.POINTER(i32)],
+        "b2_select_points": [vp, vp, i32, vp, vp, C.POINTER(i32)],
         "b2_slam_set_pose": [vp, pd],
         "b2_slam_get_pose": [vp, pd],
         "b2_icp_batch": [vp, vp, vp, i32, vp, vp, i32, i32, f64, vp, C.POINTER(IcpParams), vp],
@@ -262,6 +266,32 @@ class Engine:
         _t, tp = _dptr(T)
         self._check(self.lib.b2_transform(self.h, pts.data_ptr(), pts.shape[0], tp, out.data_ptr()))
         return out
+
+    # -- map maintenance ------------------------------------------------------
+    def radius_outlier_mask(self, pts, nb_points: int, radius: float):
+        """-> (keep uint8 [n] CUDA tensor, number kept)."""
+        pts = self._pts(pts)
+        keep = self.empty(pts.shape[0], self.torch.uint8)
+        m = C.c_int(0)
+        self._check(self.lib.b2_radius_outlier_mask(self.h, pts.data_ptr(), pts.shape[0], int(nb_points),
+                                                    float(radius), keep.data_ptr(), C.byref(m)))
+        return keep, m.value
+
+    def statistical_outlier_mask(self, pts, nb_neighbors: int, std_ratio: float, cell: float = 0.0):
+        pts = self._pts(pts)
+        keep = self.empty(pts.shape[0], self.torch.uint8)
+        m = C.c_int(0)
+        self._check(self.lib.b2_statistical_outlier_mask(self.h, pts.data_ptr(), pts.shape[0], int(nb_neighbors),
+                                                         float(std_ratio), float(cell), keep.data_ptr(), C.byref(m)))
+        return keep, m.value
+
+    def select_points(self, pts, keep):
+        pts = self._pts(pts)
+        out = self.empty_points(pts.shape[0])
+        m = C.c_int(0)
+        self._check(self.lib.b2_select_points(self.h, pts.data_ptr(), pts.shape[0], keep.data_ptr(), out.data_ptr(),
+                                              C.byref(m)))
+        return out[:m.value]
 
     # -- resident map ---------------------------------------------------------
     def map_init(self, voxel: float, origin, max_corr: float, capacity_cells: int):

@@ -414,6 +414,82 @@ int b2_transform(b2_handle h, const float* pts_dev, int n, const double* T, floa
     return B2_OK;
 }
 
+static int count_kept(Context* c, const unsigned char* keep, int n, int* n_kept) {
+    if (!n_kept) return check_status(c);
+    B2_WS(c, tmp, float4, WS_TMP_PTS2, sizeof(float4) * 4);
+    B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
+    // count through the compaction's own prefix sum (no output written: n_out only)
+    B2_WS(c, scratch, float4, WS_TMP_PTS, sizeof(float4) * (size_t)n);
+    (void)tmp;
+    B2_TRY(select_points(c, scratch, n, keep, scratch, cnt));
+    int* hn = (int*)c->host_mailbox + 720;
+    B2_CUDA_OK(c, cudaMemcpyAsync(hn, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    *n_kept = *hn;
+    return B2_OK;
+}
+
+int b2_radius_outlier_mask(b2_handle h, const float* pts_dev, int n, int nb_points, double radius,
+                           unsigned char* keep_dev, int* n_kept) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !keep_dev))) return set_error(c, B2_ERR_INVALID, "b2_radius_outlier_mask: bad arguments");
+    if (n == 0) { if (n_kept) *n_kept = 0; return B2_OK; }
+    auto body = [&]() -> int {
+        B2_TRY(radius_outlier_mask(c, (const float4*)pts_dev, n, nb_points, radius, keep_dev));
+        return count_kept(c, keep_dev, n, n_kept);
+    };
+    B2_RETRY_WIDE(c, body());
+}
+
+int b2_statistical_outlier_mask(b2_handle h, const float* pts_dev, int n, int nb_neighbors, double std_ratio,
+                                double cell, unsigned char* keep_dev, int* n_kept) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !keep_dev))) return set_error(c, B2_ERR_INVALID, "b2_statistical_outlier_mask: bad arguments");
+    if (n == 0) { if (n_kept) *n_kept = 0; return B2_OK; }
+    auto body = [&]() -> int {
+        // one coarse voxelisation gives both the bounding box (how many grid levels the k-NN sweep
+        // needs) and the density the finest cell is sized from: occupancy of 5 cm voxels -> points
+        // per m^2 of a surface-like cloud -> 9 c^2 rho ~ 6 k points in a 27-cell stencil
+        B2_WS(c, tmp, float4, WS_TMP_PTS, sizeof(float4) * (size_t)n);
+        DownsampleOut dso{tmp, nullptr, nullptr, nullptr};
+        VoxelSortOut vs;
+        B2_TRY(voxel_downsample(c, (const float4*)pts_dev, n, nullptr, nullptr, 1, 0.05, 0, nullptr, nullptr, dso, &vs));
+        int* hn = (int*)c->host_mailbox + 724;
+        VoxelPrep* hp = (VoxelPrep*)((char*)c->host_mailbox + 3072);
+        B2_CUDA_OK(c, cudaMemcpyAsync(hn, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        B2_CUDA_OK(c, cudaMemcpyAsync(hp, vs.prep, sizeof(VoxelPrep), cudaMemcpyDeviceToHost, c->stream));
+        B2_TRY(check_status(c));
+        double extent = 0.0;
+        for (int d = 0; d < 3; ++d) extent = std::fmax(extent, hp->maxb[d] - hp->minb[d]);
+        extent = extent * 1.001 + 1e-6;
+        double use_cell = cell;
+        if (!(use_cell > 0.0)) {
+            const double per_voxel = (double)n / (double)(*hn > 0 ? *hn : 1);
+            const double rho = per_voxel / (0.05 * 0.05);
+            use_cell = std::sqrt(6.0 * (double)nb_neighbors / (9.0 * rho));
+            if (use_cell < 0.002) use_cell = 0.002;
+            if (use_cell > 0.5) use_cell = 0.5;
+        }
+        B2_TRY(statistical_outlier_mask(c, (const float4*)pts_dev, n, nb_neighbors, std_ratio, use_cell, extent, keep_dev));
+        return count_kept(c, keep_dev, n, n_kept);
+    };
+    B2_RETRY_WIDE(c, body());
+}
+
+int b2_select_points(b2_handle h, const float* pts_dev, int n, const unsigned char* keep_dev, float* out_pts_dev,
+                     int* n_out) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !keep_dev || !out_pts_dev))) return set_error(c, B2_ERR_INVALID, "b2_select_points: bad arguments");
+    if (n == 0) { if (n_out) *n_out = 0; return B2_OK; }
+    B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
+    B2_TRY(select_points(c, (const float4*)pts_dev, n, keep_dev, (float4*)out_pts_dev, cnt));
+    int* hn = (int*)c->host_mailbox + 720;
+    B2_CUDA_OK(c, cudaMemcpyAsync(hn, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    if (n_out) *n_out = *hn;
+    return B2_OK;
+}
+
 int b2_map_init(b2_handle h, double voxel, const double* origin, double max_corr, long long capacity_cells) {
     CTX(h);
     return map_init(c, voxel, origin, max_corr, capacity_cells);

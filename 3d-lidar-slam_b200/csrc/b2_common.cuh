@@ -40,7 +40,7 @@ enum WsSlot : int {
     WS_GRID_ENTRIES, WS_GRID_PTS, WS_GRID_META, WS_ICP_STATE, WS_ICP_PARTIAL, WS_ICP_TICKET, WS_ICP_SYNC,
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
-    WS_CORR, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D, WS_NUM_SLOTS
+    WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu
@@ -368,6 +368,13 @@ int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev
 // b2_normals.cu
 int estimate_normals(Context* c, const float4* pts, int n_max, const int* n_dev, double radius, int max_nn,
                      float4* normals_out);
+
+// b2_filters.cu
+int radius_outlier_mask(Context* c, const float4* pts, int n, int nb_points, double radius, unsigned char* keep);
+// extent: upper bound of the cloud's largest bounding-box edge (decides the coarsest search level)
+int statistical_outlier_mask(Context* c, const float4* pts, int n, int nb_neighbors, double std_ratio, double cell,
+                             double extent, unsigned char* keep);
+int select_points(Context* c, const float4* pts, int n, const unsigned char* keep, float4* out, int* n_out_dev);
 
 // b2_map.cu
 void map_free(Context* c);

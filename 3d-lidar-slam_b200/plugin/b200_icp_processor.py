@@ -38,7 +38,7 @@ class B200ICPProcessor(ProcessPointClouds):
                  voxel_size: float = 0.02, max_correspondence_distance: float | None = None,
                  max_iteration: int = 500, relative_fitness: float = 1e-6, relative_rmse: float = 1e-6,
                  map_voxel: float | None = None, map_origin=(0.0, 0.0, 0.0), map_capacity_cells: int = 1 << 22,
-                 maintenance: str = "voxel", numpy2_projection: bool | None = None, device: int = 0,
+                 maintenance: str = "full", numpy2_projection: bool | None = None, device: int = 0,
                  logger=None):
         if mode not in ("resident", "reference"):
             raise ValueError(f"unknown mode {mode!r}")
@@ -149,15 +149,25 @@ class B200ICPProcessor(ProcessPointClouds):
         self._do_stuff()
 
     def _do_stuff(self) -> None:
-        """ICPProcessor.do_stuff (icp_processor.py:121-148): periodic 1 mm re-voxelisation (+ outlier
-        filters, which are rows f2 of the scope table and not built yet)."""
+        """ICPProcessor.do_stuff (icp_processor.py:121-148): every 10th scan (or whenever the input queue is
+        empty) re-voxelise the map at 1 mm and drop statistical outliers (45 neighbours, 3.5 sigma); every
+        40th scan use (80, 2.0) followed by the radius filter (more than 8 points within 2.3 cm)."""
         if self._maintenance == "off" or self.point_clouds_in_map < 10:
             return
         if self.point_clouds_in_map % 10 == 0 or self.data_transfer.pixel_depth_map_queue.empty():
+            eng = self._engine
+            m, _ = eng.voxel_downsample(self._raw_map, 0.001, want_keys=False)
+            m = m.contiguous()
             if self._maintenance == "full":
-                raise NotImplementedError("statistical / radius outlier removal on the GPU is not built yet")
-            self._raw_map, _ = self._engine.voxel_downsample(self._raw_map, 0.001, want_keys=False)
-            self._raw_map = self._raw_map.contiguous()
+                if self.point_clouds_in_map % 40 == 0:
+                    keep, _ = eng.statistical_outlier_mask(m, 80, 2.0)
+                    m = eng.select_points(m, keep).contiguous()
+                    keep, _ = eng.radius_outlier_mask(m, 8, 0.023)
+                    m = eng.select_points(m, keep).contiguous()
+                else:
+                    keep, _ = eng.statistical_outlier_mask(m, 45, 3.5)
+                    m = eng.select_points(m, keep).contiguous()
+            self._raw_map = m
 
 
 def _records_to_array(points) -> np.ndarray:

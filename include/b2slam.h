@@ -113,6 +113,21 @@ int b2_icp(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int 
 /* PointCloud.transform(T) (icp_processor.py:73). In-place allowed. */
 int b2_transform(b2_handle h, const float* pts_dev, int n, const double* T, float* out_pts_dev);
 
+/* ---- map maintenance (ICPProcessor.do_stuff, icp_processor.py:121-148) ---- */
+/* PointCloud.remove_radius_outlier(nb_points, radius) (icp_processor.py:139-140):
+ * keep_dev uint8 [n] = 1 where more than nb_points points (the point itself included) lie within
+ * radius (d^2 < r^2); *n_kept may be NULL. */
+int b2_radius_outlier_mask(b2_handle h, const float* pts_dev, int n, int nb_points, double radius,
+                           unsigned char* keep_dev, int* n_kept);
+/* PointCloud.remove_statistical_outlier(nb_neighbors, std_ratio) (icp_processor.py:136-137,145-146;
+ * SURVEY A.8): exact k-nearest mean distance per point, keep where 0 < mean < mu + std_ratio * sigma.
+ * cell <= 0: the search cell is sized from the cloud's density. */
+int b2_statistical_outlier_mask(b2_handle h, const float* pts_dev, int n, int nb_neighbors, double std_ratio,
+                                double cell, unsigned char* keep_dev, int* n_kept);
+/* PointCloud.select_by_index of the kept points, order preserved: out_pts_dev float32 [n,4]. */
+int b2_select_points(b2_handle h, const float* pts_dev, int n, const unsigned char* keep_dev, float* out_pts_dev,
+                     int* n_out);
+
 /* ---- resident global map ------------------------------------------------ */
 /* The reference keeps the map as a host ndarray that it re-voxelises, re-indexes and
  * re-uploads for every scan (icp_processor.py:64-65,91,103).  Here the map is a

@@ -225,7 +225,7 @@ struct KDTree {
         const Node& nd = nodes[id];
         if (nd.dim < 0) {
             for (int32_t i = nd.left; i < nd.right; ++i)
-                if (dist2(pts + 3 * (int64_t)order[i], q) <= r2) ++cnt;
+                if (dist2(pts + 3 * (int64_t)order[i], q) < r2) ++cnt;  // nanoflann RadiusResultSet: dist < radius
             return;
         }
         double v = nd.dim == 0 ? q.x : (nd.dim == 1 ? q.y : q.z);

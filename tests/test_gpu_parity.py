@@ -350,3 +350,53 @@ def test_projection_kernel_matches_host(engine):
     for numpy2, mode in ((False, "f64"), (True, "f32")):
         got = xyz(engine.project_pixels(rec, fx, fy, cx, cy, numpy2=numpy2))
         np.testing.assert_array_equal(got, synth.project_records(torch.from_numpy(rec), mode=mode).numpy())
+
+
+# ------------------------------------------------------------------ map maintenance filters (A.8)
+def _cloud_with_outliers(seed=0, n=24000):
+    rng = np.random.default_rng(seed)
+    g = rng.uniform(0, 1, size=(n, 2))
+    wall = np.stack([2.0 * g[:, 0], rng.normal(scale=0.003, size=n), 1.5 * g[:, 1]], 1)
+    floor = np.stack([2.0 * g[:, 1], 1.2 * g[:, 0], rng.normal(scale=0.003, size=n)], 1)
+    stray = rng.uniform(-0.5, 2.5, size=(300, 3))
+    far = np.array([[9.0, 9.0, 9.0], [9.02, 9.0, 9.0], [-7.0, 3.0, 1.0]])
+    return np.concatenate([wall, floor, stray, far]).astype(np.float32)
+
+
+def test_radius_outlier_filter_matches_oracle(engine):
+    pts = _cloud_with_outliers(1)
+    keep, kept = engine.radius_outlier_mask(engine.pack(pts), 8, 0.023)
+    omask = orc.radius_outlier_mask(f64(pts), 8, 0.023)
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), omask)
+    assert kept == int(omask.sum()) and 0 < kept < len(pts)
+
+
+@pytest.mark.parametrize("k,ratio", [(45, 3.5), (80, 2.0)])
+def test_statistical_outlier_filter_matches_oracle(engine, k, ratio):
+    pts = _cloud_with_outliers(2)
+    keep, kept = engine.statistical_outlier_mask(engine.pack(pts), k, ratio)
+    omask = orc.statistical_outlier_mask(f64(pts), k, ratio)
+    g = keep.cpu().numpy().astype(bool)
+    # identical except for points whose mean distance sits within rounding of the threshold
+    assert int((g != omask).sum()) <= 1, int((g != omask).sum())
+    assert abs(kept - int(omask.sum())) <= 1 and 0 < kept < len(pts)
+    # explicit (deliberately poor) cell sizes exercise the ring growth and the overflow path
+    for cell in (0.01, 0.2):
+        keep2, _ = engine.statistical_outlier_mask(engine.pack(pts[::4].copy()), k, ratio, cell=cell)
+        o2 = orc.statistical_outlier_mask(f64(pts[::4]), k, ratio)
+        assert int((keep2.cpu().numpy().astype(bool) != o2).sum()) <= 1
+
+
+def test_statistical_filter_small_cloud(engine):
+    pts = np.array([[0, 0, 0], [0.01, 0, 0], [0, 0.01, 0], [0.5, 0.5, 0.5]], dtype=np.float32)
+    keep, kept = engine.statistical_outlier_mask(engine.pack(pts), 45, 1.0)  # k > n: every point is a neighbour
+    np.testing.assert_array_equal(keep.cpu().numpy().astype(bool), orc.statistical_outlier_mask(f64(pts), 45, 1.0))
+
+
+def test_select_points_preserves_order(engine):
+    pts = _cloud_with_outliers(3)
+    keep, kept = engine.radius_outlier_mask(engine.pack(pts), 8, 0.023)
+    sel = engine.select_points(engine.pack(pts), keep)
+    engine.synchronize()
+    np.testing.assert_array_equal(xyz(sel), pts[keep.cpu().numpy().astype(bool)])
+    assert sel.shape[0] == kept

@@ -127,3 +127,19 @@ def test_streaming_replay_tracks_and_grows_the_map():
             assert proc.last_result.fitness > 0.9
     assert all(b >= a for a, b in zip(sizes, sizes[1:])) and sizes[-1] > 1.3 * sizes[0]
     assert len(proc.global_map) == sizes[-1]
+
+
+@pytest.mark.parametrize("count", [10, 40])
+def test_reference_mode_full_maintenance(count):
+    """do_stuff with the outlier filters (icp_processor.py:135-148) against the oracle sequence."""
+    scans = [s[::3].copy() for s in _scans(2)]  # thinned: the CPU oracle's 80-NN pass stays in seconds
+    proc, _ = _processor(mode="reference", max_iteration=20, maintenance="full")
+    ref = pipeline.ReferenceSequence(max_iteration=20, maintenance="full", f32_storage=True)
+    proc.construct_global_map(scans[0])
+    ref.process(scans[0])
+    proc.point_clouds_in_map = ref.point_clouds_in_map = count
+    proc.construct_global_map(scans[1])
+    ref.construct_global_map(scans[1])
+    n, n_ref = len(proc.global_map), len(ref.global_map)
+    assert 0 < n < 2 * len(scans[0])
+    assert abs(n - n_ref) <= max(3, n_ref // 2000), (n, n_ref)  # threshold-straddling points only
