@@ -24,7 +24,7 @@ EXPORTS = [
     "b2_estimate_normals", "b2_nn_search", "b2_icp", "b2_transform", "b2_map_init", "b2_map_reset",
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
-    "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points",
+    "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
 ]
 
 
@@ -90,6 +90,7 @@ def load():
         "b2_radius_outlier_mask": [vp, vp, i32, i32, f64, vp, C.POINTER(i32)],
         "b2_statistical_outlier_mask": [vp, vp, i32, i32, f64, f64, vp, C.POINTER(i32)],
         "b2_select_points": [vp, vp, i32, vp, vp, C.POINTER(i32)],
+        "b2_stencil_candidates": [vp, vp, i32, vp, i32, pd, f64, C.POINTER(i64)],
         "b2_slam_set_pose": [vp, pd],
         "b2_slam_get_pose": [vp, pd],
         "b2_icp_batch": [vp, vp, vp, i32, vp, vp, i32, i32, f64, vp, C.POINTER(IcpParams), vp],
@@ -348,11 +349,18 @@ class Engine:
                                               C.byref(params), C.byref(res) if want_result else None))
         return res
 
-    def stencil_candidates(self, src, T=None) -> int:
+    def stencil_candidates(self, src, T=None, tgt=None, cell: float = 0.0) -> int:
+        """Points under the 27-cell stencils of the (transformed) source: against the resident map, or
+        against `tgt` gridded with edge `cell`."""
         src = self._pts(src)
         _t, tp = _dptr(T)
         n = C.c_longlong(0)
-        self._check(self.lib.b2_map_stencil_candidates(self.h, src.data_ptr(), src.shape[0], tp, C.byref(n)))
+        if tgt is None:
+            self._check(self.lib.b2_map_stencil_candidates(self.h, src.data_ptr(), src.shape[0], tp, C.byref(n)))
+        else:
+            tgt = self._pts(tgt)
+            self._check(self.lib.b2_stencil_candidates(self.h, src.data_ptr(), src.shape[0], tgt.data_ptr(),
+                                                       tgt.shape[0], tp, float(cell), C.byref(n)))
         return int(n.value)
 
     def set_pose(self, T):

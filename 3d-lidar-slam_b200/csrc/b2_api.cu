@@ -550,6 +550,29 @@ int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, co
     return B2_OK;
 }
 
+int b2_stencil_candidates(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt, const double* T,
+                          double cell, long long* n_candidates) {
+    CTX(h);
+    if (ns <= 0 || nt <= 0 || !src_dev || !tgt_dev || !n_candidates || !(cell > 0.0))
+        return set_error(c, B2_ERR_INVALID, "b2_stencil_candidates: bad arguments");
+    B2_TRY(check_T(c, T, "b2_stencil_candidates"));
+    auto body = [&]() -> int {
+        double* T_dev = nullptr;
+        if (T) B2_TRY(upload_T(c, T, 7, &T_dev));
+        GridView g;
+        B2_TRY(grid_build(c, (const float4*)tgt_dev, nt, nullptr, nullptr, 1, cell, WS_GRID_ENTRIES, &g));
+        B2_WS(c, cnt, unsigned long long, WS_COUNTS, sizeof(unsigned long long) * 2);
+        B2_CUDA_OK(c, cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * 2, c->stream));
+        B2_TRY(map_stencil_count(c, (const float4*)src_dev, ns, T_dev, g, cnt));
+        unsigned long long* hc = (unsigned long long*)((char*)c->host_mailbox + 2048);
+        B2_CUDA_OK(c, cudaMemcpyAsync(hc, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        B2_TRY(check_status(c));
+        *n_candidates = (long long)*hc;
+        return B2_OK;
+    };
+    B2_RETRY_WIDE(c, body());
+}
+
 int b2_slam_set_pose(b2_handle h, const double* T) {
     CTX(h);
     if (!T) return set_error(c, B2_ERR_INVALID, "b2_slam_set_pose: NULL transform");

@@ -842,11 +842,11 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                        search_only);
 }
 
-// Candidate census of the resident-map stencil (the data-dependent term of the byte model).
+// Candidate census of the 27-cell stencil (the data-dependent term of the byte model); kind as in GridView.
 __global__ void __launch_bounds__(256)
 stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __restrict__ T,
                      const CellEntry* __restrict__ entries, const VoxEntry* __restrict__ vox, unsigned mask,
-                     const GridMeta* __restrict__ meta, unsigned long long* __restrict__ total) {
+                     const GridMeta* __restrict__ meta, int kind, unsigned long long* __restrict__ total) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * 256 + threadIdx.x) >> 5;
     if (q >= ns) return;
@@ -857,7 +857,7 @@ stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __res
     int cx = voxel_coord(P.x, meta->origin[0], meta->cell);
     int cy = voxel_coord(P.y, meta->origin[1], meta->cell);
     int cz = voxel_coord(P.z, meta->origin[2], meta->cell);
-    if (brick > 1) {
+    if (kind == 1 && brick > 1) {
         cx = floor_div(cx, brick);
         cy = floor_div(cy, brick);
         cz = floor_div(cz, brick);
@@ -865,19 +865,39 @@ stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __res
     unsigned cnt = 0;
     if (lane < 27) {
         const int nx = cx + lane / 9 - 1, ny = cy + (lane / 3) % 3 - 1, nz = cz + lane % 3 - 1;
-        const unsigned long long key = map_cell_key(nx, ny, nz);
-        if (vox) {
-            float x, y, z;
-            unsigned slot;
-            cnt = vox_lookup(vox, mask, key, x, y, z, slot) ? 1u : 0u;
+        if (kind == 0) {
+            if (nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536) {
+                const unsigned long long key = pair_cell_key(0u, nx, ny, nz);
+                const CellEntry e = grid_lookup(entries, mask, key);
+                if (e.key == key) cnt = e.cnt;
+            }
         } else {
-            const CellEntry e = grid_lookup(entries, mask, key);
-            if (e.key == key) cnt = e.cnt;
+            const unsigned long long key = map_cell_key(nx, ny, nz);
+            if (kind == 2) {
+                float x, y, z;
+                unsigned slot;
+                cnt = vox_lookup(vox, mask, key, x, y, z, slot) ? 1u : 0u;
+            } else {
+                const CellEntry e = grid_lookup(entries, mask, key);
+                if (e.key == key) cnt = e.cnt;
+            }
         }
     }
     cnt = __reduce_add_sync(kFull, cnt);
     if (lane == 0 && cnt) atomicAdd(total, (unsigned long long)cnt);
 }
+
+}  // namespace
+
+int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev, const GridView& g,
+                      unsigned long long* total_dev) {
+    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.vox,
+                                                                                  g.mask, g.meta, g.is_map, total_dev);
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
+
+namespace {
 
 template <int MODE, int KIND>
 int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max, const GridView& g,
@@ -911,14 +931,6 @@ int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max,
 }
 
 }  // namespace
-
-int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev, const GridView& g,
-                      unsigned long long* total_dev) {
-    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.is_map == 2 ? g.vox : nullptr,
-                                                                                  g.mask, g.meta, total_dev);
-    B2_LAUNCH_CHECK(c);
-    return B2_OK;
-}
 
 int icp_grid_x(int ns_max, int n_pairs) {
     // single pair: one query per 4-lane group when it fits (160 groups per CTA, one CTA per SM);

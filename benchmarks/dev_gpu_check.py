@@ -6,7 +6,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root
 sys.path.insert(0, ROOT)
 import lidar_slam_b200 as b2  # noqa: E402
 from lidar_slam_b200 import synth  # noqa: E402

@@ -162,6 +162,9 @@ int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_v
 /* Number of resident-map points inside the 27-cell stencils of the transformed source points —
  * the data-dependent term of the search's algorithmic-byte model. */
 int b2_map_stencil_candidates(b2_handle h, const float* src_dev, int ns, const double* T, long long* n_candidates);
+/* The same census for an arbitrary target cloud gridded with cell edge `cell` (pair mode). */
+int b2_stencil_candidates(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt, const double* T,
+                          double cell, long long* n_candidates);
 int b2_slam_set_pose(b2_handle h, const double* T);
 int b2_slam_get_pose(b2_handle h, double* T);
 
