@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scans-per-step", type=int, default=64)
     ap.add_argument("--pairs", type=int, default=512, help="independent pairs per rank for the batched_pairs leg")
-    ap.add_argument("--cpu-scans", type=int, default=3, help="scans timed by the CPU baseline leg")
+    ap.add_argument("--cpu-scans", type=int, default=10, help="scans timed by the CPU baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
     return ap.parse_args()
