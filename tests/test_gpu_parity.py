@@ -400,3 +400,27 @@ def test_select_points_preserves_order(engine):
     engine.synchronize()
     np.testing.assert_array_equal(xyz(sel), pts[keep.cpu().numpy().astype(bool)])
     assert sel.shape[0] == kept
+
+
+def test_batch_icp_ragged_and_empty_pairs(engine, b2):
+    """Ragged batch: a full pair, a tiny pair, a pair with an EMPTY source and a non-overlapping pair."""
+    from lidar_slam_b200 import synth
+
+    s0, t0, _ = synth.make_pair(5)
+    s0, t0 = s0.numpy()[::3].copy(), t0.numpy()[::3].copy()
+    srcs = [s0, s0[:50].copy(), np.zeros((0, 3), np.float32), (s0 + np.float32(40.0))]
+    tgts = [t0, t0, t0[:2000].copy(), t0]
+    so = np.cumsum([0] + [len(s) for s in srcs]).astype(np.int32)
+    to = np.cumsum([0] + [len(t) for t in tgts]).astype(np.int32)
+    res = engine.icp_batch(engine.pack(np.concatenate(srcs)), torch.from_numpy(so).cuda(),
+                           engine.pack(np.concatenate(tgts)), torch.from_numpy(to).cuda(), b2.make_params(0.05, 20))
+    engine.synchronize()
+    rec = b2.results_to_numpy(res)
+    for i in (0, 1, 3):
+        ores = orc.registration_icp(f64(srcs[i]), f64(tgts[i]), 0.05, max_iteration=20)
+        assert rec["iterations"][i] == ores.iterations, i
+        assert rec["fitness"][i] == ores.fitness, i
+        assert_transform_close(rec["transformation"][i], ores.transformation)
+    assert rec["fitness"][2] == 0.0 and rec["n_correspondences"][2] == 0
+    np.testing.assert_array_equal(rec["transformation"][2], np.eye(4))
+    assert rec["fitness"][3] == 0.0
