@@ -449,14 +449,26 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
                     if (kk != key[k]) continue;
                     const unsigned off = raw[k].z;
                     const int cnt = (int)raw[k].w;
-                    for (int j = 0; j < cnt; ++j) {
-                        const float4 t = __ldg(a.gpts + off + j);
-                        const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                        const int idx = __float_as_int(t.w);
-                        if (d2 < best || (d2 == best && idx < best_idx)) {
-                            best = d2;
-                            best_idx = idx;
-                            bx = t.x; by = t.y; bz = t.z;
+                    // candidates of a cell four at a time: the loads and the four distance chains are
+                    // independent (clamped index instead of predication), only the final compare/select
+                    // is sequential
+                    for (int j = 0; j < cnt; j += 4) {
+                        float4 t[4];
+                        double d2[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) t[u] = __ldg(a.gpts + off + min(j + u, cnt - 1));
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            d2[u] = dist2_strict(Px, Py, Pz, (double)t[u].x, (double)t[u].y, (double)t[u].z);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int idx = __float_as_int(t[u].w);
+                            // a clamped duplicate re-offers the cell's last point: same (d2, idx), never wins twice
+                            if (d2[u] < best || (d2[u] == best && idx < best_idx)) {
+                                best = d2[u];
+                                best_idx = idx;
+                                bx = t[u].x; by = t[u].y; bz = t[u].z;
+                            }
                         }
                     }
                 }
