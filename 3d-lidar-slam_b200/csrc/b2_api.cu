@@ -595,18 +595,19 @@ int b2_slam_get_pose(b2_handle h, double* T) {
 
 // Everything of one scan step after the scan sits in the fixed device buffer `scan`:
 // down-sample -> ICP against the resident map (pose chained on the device) -> fuse.
-static int slam_body(Context* c, const float4* scan, int n, double ds_voxel, const b2_icp_params* params,
-                     bool map_empty) {
+static int slam_body(Context* c, const float4* scan, int n, const int* n_dev, double ds_voxel,
+                     const b2_icp_params* params, bool map_empty) {
+    // n is the capacity the kernels are launched for; the live point count sits in *n_dev
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
     if (!map_empty) {
         const float4* src = scan;
-        const int* ns_dev = nullptr;
+        const int* ns_dev = n_dev;
         if (ds_voxel > 0.0) {
             B2_WS(c, sdown, float4, WS_SRC_DOWN, sizeof(float4) * (size_t)n);
             DownsampleOut dso{sdown, nullptr, nullptr, nullptr};
             VoxelSortOut vs;
-            B2_TRY(voxel_downsample(c, scan, n, nullptr, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
+            B2_TRY(voxel_downsample(c, scan, n, n_dev, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
             // keep the voxel count where later sorts cannot overwrite it
             B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
             B2_CUDA_OK(c, cudaMemcpyAsync(cnt, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
@@ -620,7 +621,7 @@ static int slam_body(Context* c, const float4* scan, int n, double ds_voxel, con
         copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose);
         B2_LAUNCH_CHECK(c);
     }
-    B2_TRY(map_fuse(c, scan, n, nullptr, pose));
+    B2_TRY(map_fuse(c, scan, n, n_dev, pose));
     return B2_OK;
 }
 
@@ -628,12 +629,13 @@ static int slam_body(Context* c, const float4* scan, int n, double ds_voxel, con
 // most of the inter-kernel gap.  A graph is keyed by everything baked into its nodes (sizes,
 // parameters, workspace/map addresses); the first call with a new key runs eagerly (it sizes the
 // workspaces), the second captures, later calls replay.
-static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_voxel, const b2_icp_params* params) {
+static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n_dev, double ds_voxel,
+                             const b2_icp_params* params) {
     static const bool no_graph = getenv("B2_NO_GRAPH") != nullptr;
     ScanGraph& sg = c->scan_graph;
     const bool same = sg.n == n && sg.ds_voxel == ds_voxel && sg.scan == scan &&
                       std::memcmp(&sg.params, params, sizeof(*params)) == 0 && sg.generation == c->ws_generation;
-    if (no_graph) return slam_body(c, scan, n, ds_voxel, params, false);
+    if (no_graph) return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
     if (same && sg.exec) {
         B2_CUDA_OK(c, cudaGraphLaunch(sg.exec, c->stream));
         c->launches += sg.kernel_nodes;
@@ -642,7 +644,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_vo
     if (!same) {  // new shape: eager run, remember the key
         if (sg.exec) cudaGraphExecDestroy(sg.exec);
         sg.exec = nullptr;
-        B2_TRY(slam_body(c, scan, n, ds_voxel, params, false));
+        B2_TRY(slam_body(c, scan, n, n_dev, ds_voxel, params, false));
         sg.n = n; sg.ds_voxel = ds_voxel; sg.scan = scan; sg.params = *params; sg.generation = c->ws_generation;
         return B2_OK;
     }
@@ -650,7 +652,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_vo
     const unsigned long long launches_before = c->launches;
     B2_CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     c->capturing = true;
-    int rc = slam_body(c, scan, n, ds_voxel, params, false);
+    int rc = slam_body(c, scan, n, n_dev, ds_voxel, params, false);
     c->capturing = false;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
@@ -660,7 +662,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_vo
         sg.n = -1;  // do not try again with this key until it changes
         c->launches = launches_before;
         if (rc != B2_OK && rc != B2_ERR_CUDA) return rc;
-        return slam_body(c, scan, n, ds_voxel, params, false);
+        return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
     }
     e = cudaGraphInstantiate(&sg.exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -668,7 +670,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_vo
         sg.exec = nullptr;
         sg.n = -1;
         c->launches = launches_before;
-        return slam_body(c, scan, n, ds_voxel, params, false);
+        return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
     }
     sg.kernel_nodes = (int)(c->launches - launches_before);
     c->launches = launches_before + sg.kernel_nodes;
@@ -678,18 +680,25 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, double ds_vo
 
 static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
                           const b2_icp_params* params, b2_icp_result* out, bool map_empty) {
-    // the scan always lands in one fixed device buffer so that the step's graph can be replayed
-    B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)n);
+    // The scan always lands in one fixed device buffer, kernels are launched for a capacity bucket and
+    // read the live point count from device memory: the step's graph is replayed for every scan size
+    // of the bucket (real scans drop a varying number of invalid pixels).
+    const int cap = (n + 8191) / 8192 * 8192;
+    B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)cap);
+    B2_WS(c, n_dev, int, WS_SCAN_COUNT, sizeof(int) * 4);
+    int* hn = (int*)c->host_mailbox + 760 + (c->scan_seq++ & 7);  // small ring: the copy is asynchronous
+    *hn = n;
+    B2_CUDA_OK(c, cudaMemcpyAsync(n_dev, hn, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (scan_dev) {
         B2_CUDA_OK(c, cudaMemcpyAsync(scan, scan_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     } else {
-        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)n);
+        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)cap);
         B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
         pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);
         B2_LAUNCH_CHECK(c);
     }
-    if (map_empty) B2_TRY(slam_body(c, scan, n, ds_voxel, params, true));
-    else B2_TRY(slam_body_graphed(c, scan, n, ds_voxel, params));
+    if (map_empty) B2_TRY(slam_body(c, scan, cap, n_dev, ds_voxel, params, true));
+    else B2_TRY(slam_body_graphed(c, scan, cap, n_dev, ds_voxel, params));
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
     if (out) {

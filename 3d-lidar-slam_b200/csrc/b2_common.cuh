@@ -40,7 +40,7 @@ enum WsSlot : int {
     WS_GRID_ENTRIES, WS_GRID_PTS, WS_GRID_META, WS_ICP_STATE, WS_ICP_PARTIAL, WS_ICP_TICKET, WS_ICP_SYNC,
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
-    WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D, WS_NUM_SLOTS
+    WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_SCAN_COUNT, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu
@@ -69,6 +69,7 @@ struct Context {
     unsigned long long launches = 0;  // kernels launched through this context
     unsigned long long ws_generation = 0;  // bumped whenever a workspace / map buffer is (re)allocated
     bool capturing = false;                // inside stream capture: no allocation, no synchronisation
+    unsigned scan_seq = 0;                 // scans submitted (indexes the pinned count ring)
     ScanGraph scan_graph;
 };
 

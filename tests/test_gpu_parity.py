@@ -424,3 +424,28 @@ def test_batch_icp_ragged_and_empty_pairs(engine, b2):
     assert rec["fitness"][2] == 0.0 and rec["n_correspondences"][2] == 0
     np.testing.assert_array_equal(rec["transformation"][2], np.eye(4))
     assert rec["fitness"][3] == 0.0
+
+
+def test_slam_sequence_with_varying_scan_sizes(engine, b2):
+    """Real scans keep ~half of the pixels (ARDepthViewController.swift:112), a different count every frame:
+    the graph-replayed step reads the live count from device memory and must still match the oracle."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(21, length=12.0)
+    poses = synth.corridor_trajectory(scene, 7, seed=5)
+    origin = np.array([-20.0, -20.0, -20.0])
+    engine.map_init(0.05, origin, 0.05, 1 << 18)
+    ref = pipeline.ResidentSequence(0.05, origin, ds_voxel=0.02, max_corr=0.05, max_iteration=25)
+    prm = b2.make_params(0.05, 25)
+    sizes = []
+    for k, pose in enumerate(poses):
+        scan = synth.render_scan(scene, pose, seed=300 + k, keep_prob=0.5).numpy()
+        sizes.append(len(scan))
+        res = engine.slam_scan(scan, 0.02, prm)
+        ores = ref.process(scan)
+        if k == 0:
+            continue
+        assert res.iterations == ores.iterations, k
+        assert res.n_correspondences == int((ores.correspondence >= 0).sum())
+        assert_transform_close(res.matrix(), ores.transformation)
+    assert len(set(sizes)) == len(sizes) and max(sizes) < 30000
