@@ -90,6 +90,25 @@ class B200ICPProcessor(ProcessPointClouds):
         y = (r[:, 1] - self.cy) * r[:, 2] / self.fy
         return np.stack([x, y, r[:, 2]], axis=1).astype(np.float32)
 
+    def process(self) -> None:
+        """ProcessPointClouds.process (generic_point_cloud_processor.py:111-126) with the projection fused
+        into the upload: the (x_px, y_px, depth) records go to the device as they are and
+        ``b2_project_pixels`` back-projects them there, so the 49k-iteration Python loop of
+        the reference — and any host-side array of metric points — disappears from the per-scan path."""
+        scan = self.data_transfer.pixel_depth_map_queue.get()
+        self.logger.debug(f"{len(scan)} points received from queue")
+        if scan is not None:
+            self.logger.info(f"pcs processed so far: {self.point_clouds_in_map}")
+            rec = np.ascontiguousarray(_records_to_array(scan), dtype=np.float32)
+            del scan
+            pts4 = self._engine.project_pixels(rec, self.fx, self.fy, self.cx, self.cy, numpy2=self._numpy2)
+            self._map_cache = None
+            if self._mode == "resident":
+                self._construct_resident(None, pts4)
+            else:
+                self._construct_reference(pts4)
+            self.point_clouds_in_map += 1
+
     def construct_global_map(self, points: np.ndarray) -> None:
         """ICPProcessor.construct_global_map (icp_processor.py:43-75)."""
         pts = np.ascontiguousarray(points, dtype=np.float32)
@@ -114,13 +133,16 @@ class B200ICPProcessor(ProcessPointClouds):
         super().reset()
 
     # -- resident mode --------------------------------------------------------
-    def _construct_resident(self, pts: np.ndarray) -> None:
+    def _construct_resident(self, pts, pts4=None) -> None:
         eng = self._engine
         if not self._resident_ready:
             eng.map_init(self._map_voxel, self._map_origin, self._max_corr, self._map_capacity)
             self._resident_ready = True
         first = self.point_clouds_in_map == 0
-        res = eng.slam_scan(pts, self._voxel, self._params)
+        if pts4 is not None:
+            res = eng.slam_scan_dev(pts4, self._voxel, self._params, want_result=True)
+        else:
+            res = eng.slam_scan(pts, self._voxel, self._params)
         if first:
             self.point_clouds_in_map += 1  # icp_processor.py:54 (the caller increments once more)
             return

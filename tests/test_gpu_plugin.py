@@ -143,3 +143,23 @@ def test_reference_mode_full_maintenance(count):
     n, n_ref = len(proc.global_map), len(ref.global_map)
     assert 0 < n < 2 * len(scans[0])
     assert abs(n - n_ref) <= max(3, n_ref // 2000), (n, n_ref)  # threshold-straddling points only
+
+
+def test_process_with_fused_projection_equals_host_projection():
+    """process() (records -> device projection -> registration) == construct_global_map(project_pixel_to_3d(records))."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(6, length=10.0)
+    poses = synth.corridor_trajectory(scene, 3, seed=6, step=0.02)
+    recs = [synth.scan_records(synth.render_depth(scene, p, seed=90 + k), keep_prob=0.6, seed=k).numpy()
+            for k, p in enumerate(poses)]
+    a, dta = _processor(mode="resident", max_iteration=30, map_voxel=0.05)
+    b, _ = _processor(mode="resident", max_iteration=30, map_voxel=0.05)
+    for r in recs:
+        dta.pixel_depth_map_queue.put(r)
+        a.process()
+        b.construct_global_map(b.project_pixel_to_3d(r))
+        b.point_clouds_in_map += 1
+    assert a.point_clouds_in_map == b.point_clouds_in_map == 4
+    np.testing.assert_array_equal(a.previous_transformation[-1], b.previous_transformation[-1])
+    np.testing.assert_array_equal(a.global_map, b.global_map)
