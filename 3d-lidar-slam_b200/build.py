@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2slam.so")
-SOURCES = ["b2_sort.cu", "b2_voxel.cu", "b2_grid.cu", "b2_icp.cu", "b2_normals.cu", "b2_filters.cu", "b2_map.cu", "b2_api.cu"]
+SOURCES = ["b2_sort.cu", "b2_voxel.cu", "b2_voxel_cluster.cu", "b2_grid.cu", "b2_icp.cu", "b2_normals.cu", "b2_filters.cu", "b2_map.cu", "b2_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -334,6 +334,12 @@ int voxel_downsample(Context* c, const float4* pts, int n_max, const int* n_dev,
                      int n_clouds, double voxel, int origin_mode, const double* origin_host, const double* T_dev,
                      DownsampleOut out, VoxelSortOut* vs_out);
 
+// b2_voxel_cluster.cu — single-launch (8-CTA cluster) variant for one cloud of <= 65,536 points
+bool voxel_small_applicable(int n_max, int n_clouds);
+int voxel_small(Context* c, const float4* pts, int n_max, const int* n_dev, double voxel, int origin_mode,
+                const double* origin_host, const double* T_dev, bool do_centroid, DownsampleOut out,
+                VoxelSortOut* vs_out);
+
 // b2_grid.cu — uniform grid (cell hash) over n_clouds concatenated target clouds.
 struct GridView {
     CellEntry* entries;
