@@ -16,6 +16,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -104,6 +105,33 @@ void* ws_get(Context* c, int slot, size_t bytes);  // nullptr on failure (error 
     if (!var) return B2_ERR_CUDA
 
 inline int div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// Launch with programmatic stream serialisation: the grid may be scheduled while its predecessor in
+// the stream is still draining (the launch latency of the ~60 small kernels of a scan step overlaps
+// with the previous kernel's tail).  Every kernel launched this way begins with pdl_enter().
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+    static const bool off = getenv("B2_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+// First statement of a pdl_launch'ed kernel: let the successor be scheduled, then wait until the
+// predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // device-side structs

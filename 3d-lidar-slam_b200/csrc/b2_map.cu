@@ -77,6 +77,7 @@ map_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums,
                  unsigned char* __restrict__ lid, float4* __restrict__ cent, double* __restrict__ acc,
                  long long* __restrict__ counters, int brick, int cap_slots, int lut_stride,
                  unsigned long long max_cells, int* __restrict__ dev_status) {
+    pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
     if (j >= ctl->nseg) return;
     const int kx = keys3[3 * j], ky = keys3[3 * j + 1], kz = keys3[3 * j + 2];
@@ -163,6 +164,7 @@ __global__ void __launch_bounds__(kBlock)
 vox_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums, const SortCtl* __restrict__ ctl,
                  VoxEntry* __restrict__ vox, unsigned mask, double* __restrict__ acc,
                  long long* __restrict__ counters, unsigned long long max_cells, int* __restrict__ dev_status) {
+    pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
     if (j >= ctl->nseg) return;
     const int kx = keys3[3 * j], ky = keys3[3 * j + 1], kz = keys3[3 * j + 2];
@@ -398,14 +400,13 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
     B2_TRY(voxel_downsample(c, pts, n_max, n_dev, nullptr, 1, m->voxel, /*origin_mode=*/1, m->origin, T_dev, out, &vs));
     const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
     if (m->brick == 1)
-        vox_merge_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(dkeys, dsums, vs.ctl, m->vox, m->capacity - 1,
-                                                                         m->acc, m->counters, max_cells,
-                                                                         c->dev_status);
+        pdl_launch(vox_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
+                   (const double*)dsums, (const SortCtl*)vs.ctl, m->vox, m->capacity - 1, m->acc, m->counters,
+                   max_cells, c->dev_status);
     else
-        map_merge_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(dkeys, dsums, vs.ctl, m->entries,
-                                                                         m->capacity - 1, m->lut, m->lid, m->cent,
-                                                                         m->acc, m->counters, m->brick, m->cap_slots,
-                                                                         m->lut_stride, max_cells, c->dev_status);
+        pdl_launch(map_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
+                   (const double*)dsums, (const SortCtl*)vs.ctl, m->entries, m->capacity - 1, m->lut, m->lid, m->cent,
+                   m->acc, m->counters, m->brick, m->cap_slots, m->lut_stride, max_cells, c->dev_status);
     B2_LAUNCH_CHECK(c);
     m->host_voxels_bound += n_max;
     return B2_OK;

@@ -35,6 +35,7 @@ __device__ __forceinline__ void block_range(int n, int& begin, int& end) {
 __global__ void __launch_bounds__(kThreads)
 sort_hist_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
                  const SortCtl* __restrict__ ctl, int pass, unsigned* __restrict__ hist) {
+    pdl_enter();
     if (pass >= ctl->npasses) return;
     const unsigned long long* in = (pass & 1) ? keysB : keysA;
     __shared__ unsigned sh[256];
@@ -54,6 +55,7 @@ sort_hist_kernel(const unsigned long long* __restrict__ keysA, const unsigned lo
 // Exclusive scan of `total` counters in place, one CTA of 1024 threads.
 __global__ void __launch_bounds__(1024)
 sort_scan_kernel(unsigned* __restrict__ hist, int total, const SortCtl* __restrict__ ctl, int pass) {
+    pdl_enter();
     if (pass >= ctl->npasses) return;
     __shared__ unsigned warp_sums[32];
     const int per = (total + 1023) / 1024;
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(kThreads)
 sort_scatter_kernel(unsigned long long* keysA, unsigned long long* keysB, unsigned* valsA, unsigned* valsB,
                     const SortCtl* __restrict__ ctl, int pass, const unsigned* __restrict__ hist,
                     int vals_implicit, int fused_scan) {
+    pdl_enter();
     if (pass >= ctl->npasses) return;
     const bool odd = pass & 1;
     const unsigned long long* __restrict__ kin = odd ? keysB : keysA;
@@ -204,14 +207,15 @@ int radix_sort_pairs(Context* c, unsigned long long* keysA, unsigned long long* 
     B2_WS(c, hist, unsigned, WS_HIST, sizeof(unsigned) * 256 * (size_t)kMaxBlocks);
     const int fused_scan = nblocks <= 64;
     for (int p = 0; p < max_passes; ++p) {
-        sort_hist_kernel<<<nblocks, kThreads, 0, c->stream>>>(keysA, keysB, ctl, p, hist);
+        pdl_launch(sort_hist_kernel, dim3(nblocks), dim3(kThreads), c->stream, (const unsigned long long*)keysA,
+                   (const unsigned long long*)keysB, ctl, p, hist);
         B2_LAUNCH_CHECK(c);
         if (!fused_scan) {
-            sort_scan_kernel<<<1, 1024, 0, c->stream>>>(hist, 256 * nblocks, ctl, p);
+            pdl_launch(sort_scan_kernel, dim3(1), dim3(1024), c->stream, hist, 256 * nblocks, ctl, p);
             B2_LAUNCH_CHECK(c);
         }
-        sort_scatter_kernel<<<nblocks, kThreads, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, p, hist, 1,
-                                                                  fused_scan);
+        pdl_launch(sort_scatter_kernel, dim3(nblocks), dim3(kThreads), c->stream, keysA, keysB, valsA, valsB, ctl, p,
+                   (const unsigned*)hist, 1, fused_scan);
         B2_LAUNCH_CHECK(c);
     }
     return B2_OK;

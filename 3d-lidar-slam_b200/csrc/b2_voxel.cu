@@ -55,6 +55,7 @@ __device__ __forceinline__ double warp_max(double v) {
 __global__ void __launch_bounds__(kBlock)
 bbox_kernel(const float4* __restrict__ pts, const int* __restrict__ offs, const int* __restrict__ n_dev, int n_max,
             const double* __restrict__ T, unsigned long long* __restrict__ bbox) {
+    pdl_enter();
     const int cloud = blockIdx.y;
     int b, e;
     cloud_range(offs, n_dev, n_max, cloud, b, e);
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(kBlock)
 prep_kernel(const unsigned long long* __restrict__ bbox, const int* __restrict__ offs, const int* __restrict__ n_dev,
             int n_max, int n_clouds, double voxel, int origin_mode, double ox, double oy, double oz,
             int max_passes, VoxelPrep* __restrict__ prep, SortCtl* __restrict__ ctl, int* __restrict__ dev_status) {
+    pdl_enter();
     __shared__ int sbits[3];
     __shared__ int sstatus;
     if (threadIdx.x < 3) sbits[threadIdx.x] = 0;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(kBlock)
 keys_kernel(const float4* __restrict__ pts, const int* __restrict__ offs, int n_clouds, double voxel,
             const double* __restrict__ T, const VoxelPrep* __restrict__ prep, const SortCtl* __restrict__ ctl,
             unsigned long long* __restrict__ keys) {
+    pdl_enter();
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= ctl->n) return;
     const int cloud = (n_clouds > 1) ? find_cloud(offs, n_clouds, i) : 0;
@@ -201,6 +204,7 @@ __device__ __forceinline__ void seg_block_range(int n, int& begin, int& end) {
 __global__ void __launch_bounds__(kBlock)
 seg_count_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
                  const SortCtl* __restrict__ ctl, int* __restrict__ blockcnt) {
+    pdl_enter();
     const unsigned long long* keys = (ctl->npasses & 1) ? keysB : keysA;
     int begin, end;
     seg_block_range(ctl->n, begin, end);
@@ -222,6 +226,7 @@ __global__ void __launch_bounds__(kBlock)
 seg_write_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
                  SortCtl* __restrict__ ctl, const int* __restrict__ blockcnt, int* __restrict__ seg_start,
                  int* __restrict__ cloud_out_offs, int n_clouds) {
+    pdl_enter();
     const unsigned long long* keys = (ctl->npasses & 1) ? keysB : keysA;
     const int n = ctl->n;
     const int shift = ctl->bits[0] + ctl->bits[1] + ctl->bits[2];
@@ -304,6 +309,7 @@ centroid_kernel(const float4* __restrict__ pts, const int* __restrict__ offs, in
                 const SortCtl* __restrict__ ctl, const VoxelPrep* __restrict__ prep,
                 const int* __restrict__ seg_start, const double* __restrict__ T, float4* __restrict__ out_pts,
                 int* __restrict__ out_keys, double* __restrict__ out_sums) {
+    pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
     const int nseg = ctl->nseg;
     if (j >= nseg) return;
@@ -375,25 +381,26 @@ int voxel_sort(Context* c, const float4* pts, int n_max, const int* n_dev, const
     B2_CUDA_OK(c, cudaMemsetAsync(bbox, 0xFF, sizeof(unsigned long long) * 6 * (size_t)n_clouds, c->stream));
     int per_cloud = n_max / n_clouds + 1;
     dim3 bgrid(max(1, min(div_up(per_cloud, kBlock * 4), n_clouds > 1 ? 8 : kSMs * 2)), n_clouds);
-    bbox_kernel<<<bgrid, kBlock, 0, c->stream>>>(pts, cloud_offsets, n_dev, n_max, T_dev, bbox);
+    pdl_launch(bbox_kernel, bgrid, dim3(kBlock), c->stream, pts, cloud_offsets, n_dev, n_max, T_dev, bbox);
     B2_LAUNCH_CHECK(c);
     double o[3] = {0, 0, 0};
     if (origin_mode == 1) {
         if (!origin_host) return set_error(c, B2_ERR_INVALID, "explicit origin requested but origin is NULL");
         o[0] = origin_host[0]; o[1] = origin_host[1]; o[2] = origin_host[2];
     }
-    prep_kernel<<<1, kBlock, 0, c->stream>>>(bbox, cloud_offsets, n_dev, n_max, n_clouds, voxel, origin_mode, o[0],
-                                             o[1], o[2], c->sort_passes_hint, prep, ctl, c->dev_status);
+    pdl_launch(prep_kernel, dim3(1), dim3(kBlock), c->stream, bbox, cloud_offsets, n_dev, n_max, n_clouds, voxel,
+               origin_mode, o[0], o[1], o[2], c->sort_passes_hint, prep, ctl, c->dev_status);
     B2_LAUNCH_CHECK(c);
-    keys_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(pts, cloud_offsets, n_clouds, voxel, T_dev, prep,
-                                                                 ctl, keysA);
+    pdl_launch(keys_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, pts, cloud_offsets, n_clouds, voxel,
+               T_dev, (const VoxelPrep*)prep, (const SortCtl*)ctl, keysA);
     B2_LAUNCH_CHECK(c);
     B2_TRY(radix_sort_pairs(c, keysA, keysB, valsA, valsB, ctl, n_max, c->sort_passes_hint));
     int sblocks = min(kSegBlocks, div_up(n_max, kBlock));
-    seg_count_kernel<<<sblocks, kBlock, 0, c->stream>>>(keysA, keysB, ctl, blockcnt);
+    pdl_launch(seg_count_kernel, dim3(sblocks), dim3(kBlock), c->stream, (const unsigned long long*)keysA,
+               (const unsigned long long*)keysB, (const SortCtl*)ctl, blockcnt);
     B2_LAUNCH_CHECK(c);
-    seg_write_kernel<<<sblocks, kBlock, 0, c->stream>>>(keysA, keysB, ctl, blockcnt, seg_start, cloud_out_offs,
-                                                        n_clouds);
+    pdl_launch(seg_write_kernel, dim3(sblocks), dim3(kBlock), c->stream, (const unsigned long long*)keysA,
+               (const unsigned long long*)keysB, ctl, (const int*)blockcnt, seg_start, cloud_out_offs, n_clouds);
     B2_LAUNCH_CHECK(c);
     out->keysA = keysA; out->keysB = keysB; out->valsA = valsA; out->valsB = valsB;
     out->ctl = ctl; out->prep = prep; out->seg_start = seg_start;
@@ -408,9 +415,10 @@ int voxel_downsample(Context* c, const float4* pts, int n_max, const int* n_dev,
     VoxelSortOut vs;
     B2_TRY(voxel_sort(c, pts, n_max, n_dev, cloud_offsets_in, n_clouds, voxel, origin_mode, origin_host, T_dev,
                       out.cloud_offsets, &vs));
-    centroid_kernel<<<div_up(n_max, kBlock), kBlock, 0, c->stream>>>(pts, cloud_offsets_in, n_clouds, vs.keysA,
-                                                                     vs.keysB, vs.valsA, vs.valsB, vs.ctl, vs.prep,
-                                                                     vs.seg_start, T_dev, out.pts, out.keys, out.sums);
+    pdl_launch(centroid_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, pts, cloud_offsets_in, n_clouds,
+               (const unsigned long long*)vs.keysA, (const unsigned long long*)vs.keysB, (const unsigned*)vs.valsA,
+               (const unsigned*)vs.valsB, (const SortCtl*)vs.ctl, (const VoxelPrep*)vs.prep, (const int*)vs.seg_start,
+               T_dev, out.pts, out.keys, out.sums);
     B2_LAUNCH_CHECK(c);
     if (vs_out) *vs_out = vs;
     return B2_OK;
