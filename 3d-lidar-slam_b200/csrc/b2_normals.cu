@@ -6,12 +6,13 @@
 // included — feed nine cumulants; the covariance's smallest-eigenvalue
 // eigenvector is the normal ((0,0,1) when fewer than three neighbours).
 //
-// One warp serves 32 consecutive points: for each, 27 lanes probe the stencil
-// cells of a uniform grid (cell = radius) in parallel, the lanes then stride the
-// candidate points (coalesced float4 runs), and a fixed-order shuffle tree folds
-// the cumulants.  When more than max_nn neighbours fall inside the radius (rare:
-// max_nn = 20 at the reference's settings) a bit-wise bisection on the fp64
-// distance pattern finds the max_nn-th nearest exactly (ties -> lowest index).
+// One warp serves 32 consecutive points, four at a time: an 8-lane group per point,
+// each lane probing 3-4 of the 27 stencil cells of a uniform grid (cell = radius)
+// with its hash probes in flight together, folding the cumulants of its own cells'
+// points and a 3-step shuffle butterfly folding the group.  When more than max_nn
+// neighbours fall inside the radius (rare: max_nn = 20 at the reference's settings)
+// a bit-wise bisection on the fp64 distance pattern finds the max_nn-th nearest
+// exactly (ties -> lowest index) inside the group.
 // Finally every lane solves its own point's 3x3 symmetric eigenproblem (cyclic
 // Jacobi, fp64), so the dense algebra runs 32-wide and the float4 normals are
 // written coalesced.
@@ -34,7 +35,8 @@ __device__ void smallest_eigenvector_sym3(double a00, double a01, double a02, do
     const double scale = fabs(a00) + fabs(a11) + fabs(a22) + fabs(a01) + fabs(a02) + fabs(a12);
     for (int sweep = 0; sweep < 30; ++sweep) {
         const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
-        if (!(off > 1e-18 * scale)) break;
+        // a few ulp: a tighter bound is below the rounding noise of the rotations and never settles
+        if (!(off > 4e-16 * scale)) break;
 #pragma unroll
         for (int pq = 0; pq < 3; ++pq) {
             const int p = pq == 2 ? 1 : 0;
@@ -76,176 +78,247 @@ __device__ void smallest_eigenvector_sym3(double a00, double a01, double a02, do
     n[0] = x / nn; n[1] = y / nn; n[2] = z / nn;
 }
 
-__device__ __forceinline__ int warp_owner(int incl, int c) {
-    int l = 0;
+constexpr int kGroup = 8;     // lanes per query
+constexpr int kCellsPerLane = 4;  // ceil(27 / 8)
+constexpr int kStage = 64;        // in-radius candidates a group can rank in shared memory
+
+// Walk the candidates of this lane's stencil cells and fold those admitted by `take(d2 bits, idx)`.
+template <typename Take>
+__device__ __forceinline__ void fold_candidates(const uint4 (&raw)[kCellsPerLane], const bool (&hit)[kCellsPerLane],
+                                                const float4* __restrict__ gpts, double Px, double Py, double Pz,
+                                                Take take, int& cnt, double (&cum)[9]) {
 #pragma unroll
-    for (int step = 16; step >= 1; step >>= 1) {
-        int v = __shfl_sync(kFull, incl, (l + step - 1) & 31);
-        if (v <= c) l += step;
+    for (int k = 0; k < kCellsPerLane; ++k) {
+        if (!hit[k]) continue;
+        const unsigned off = raw[k].z;
+        const int n = (int)raw[k].w;
+        for (int j = 0; j < n; ++j) {
+            const float4 t = __ldg(gpts + off + j);
+            const double x = t.x, y = t.y, z = t.z;
+            const double d2 = dist2_strict(Px, Py, Pz, x, y, z);
+            if (take((unsigned long long)__double_as_longlong(d2), __float_as_int(t.w))) {
+                ++cnt;
+                cum[0] += x; cum[1] += y; cum[2] += z;
+                cum[3] += x * x; cum[4] += x * y; cum[5] += x * z;
+                cum[6] += y * y; cum[7] += y * z; cum[8] += z * z;
+            }
+        }
     }
-    return l;
+}
+
+template <typename Pred>
+__device__ __forceinline__ int count_candidates(const uint4 (&raw)[kCellsPerLane], const bool (&hit)[kCellsPerLane],
+                                                const float4* __restrict__ gpts, double Px, double Py, double Pz,
+                                                Pred pred) {
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kCellsPerLane; ++k) {
+        if (!hit[k]) continue;
+        const unsigned off = raw[k].z;
+        const int n = (int)raw[k].w;
+        for (int j = 0; j < n; ++j) {
+            const float4 t = __ldg(gpts + off + j);
+            const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
+            c += pred((unsigned long long)__double_as_longlong(d2), __float_as_int(t.w)) ? 1 : 0;
+        }
+    }
+    return c;
+}
+
+__device__ __forceinline__ int group_sum(int v, unsigned gmask) {
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
 }
 
 __global__ void __launch_bounds__(kThreads)
 normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max,
                const CellEntry* __restrict__ entries, unsigned mask, const float4* __restrict__ gpts,
                const GridMeta* __restrict__ meta, double radius, int max_nn, float4* __restrict__ normals) {
+    // staging area of a group for the capped case: (d2 bit pattern, index, position) of its in-radius
+    // candidates, ranked against each other on chip
+    __shared__ unsigned long long s_d2[kThreads / kGroup][kStage];
+    __shared__ int2 s_ip[kThreads / kGroup][kStage];
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     const int lane = threadIdx.x & 31;
+    const int g = lane & (kGroup - 1), gi = lane / kGroup;  // lane in group, group in warp
+    const int gslot = threadIdx.x / kGroup;
+    const unsigned gmask = ((1u << kGroup) - 1u) << (gi * kGroup);
     const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int warp_stride = gridDim.x * kWarps;
     const double r2 = dmul(radius, radius);
     const double ox = meta->origin[0], oy = meta->origin[1], oz = meta->origin[2], cell = meta->cell;
-    const int dx = lane / 9 - 1, dy = (lane / 3) % 3 - 1, dz = lane % 3 - 1;
     const unsigned long long r2bits = (unsigned long long)__double_as_longlong(r2);
 
+    // a warp owns 32 consecutive points: 8 rounds of 4 concurrent group searches, then every lane
+    // solves the eigenproblem of "its" point so the dense algebra runs 32-wide
     for (int base = warp_global * 32; base < n; base += warp_stride * 32) {
         double mine[9];
         int mine_k = 0;
 #pragma unroll
         for (int t = 0; t < 9; ++t) mine[t] = 0.0;
-        const int qn = min(32, n - base);
-        for (int qi = 0; qi < qn; ++qi) {
-            const float4 p = __ldg(pts + base + qi);
-            const double Px = p.x, Py = p.y, Pz = p.z;
-            const int cx = voxel_coord(Px, ox, cell), cy = voxel_coord(Py, oy, cell), cz = voxel_coord(Pz, oz, cell);
-            unsigned off = 0;
+        for (int r = 0; r < 32 / (32 / kGroup); ++r) {
+            const int q = base + r * (32 / kGroup) + gi;
+            const bool valid = q < n;
+            double Px = 0.0, Py = 0.0, Pz = 0.0;
+            int cx = 0, cy = 0, cz = 0;
+            if (g == 0 && valid) {
+                const float4 p = __ldg(pts + q);
+                Px = p.x; Py = p.y; Pz = p.z;
+                cx = voxel_coord(Px, ox, cell);
+                cy = voxel_coord(Py, oy, cell);
+                cz = voxel_coord(Pz, oz, cell);
+            }
+            const int lead = gi * kGroup;
+            Px = __shfl_sync(kFull, Px, lead);
+            Py = __shfl_sync(kFull, Py, lead);
+            Pz = __shfl_sync(kFull, Pz, lead);
+            cx = __shfl_sync(kFull, cx, lead);
+            cy = __shfl_sync(kFull, cy, lead);
+            cz = __shfl_sync(kFull, cz, lead);
+
+            uint4 raw[kCellsPerLane];
+            bool hit[kCellsPerLane];
+            unsigned long long key[kCellsPerLane];
+            unsigned hpos[kCellsPerLane];
+#pragma unroll
+            for (int k = 0; k < kCellsPerLane; ++k) {
+                const int c = g + kGroup * k;
+                const int c3 = (c * 171) >> 9, c9 = (c * 57) >> 9;
+                const int nx = cx + c9 - 1, ny = cy + (c3 - 3 * c9) - 1, nz = cz + (c - 3 * c3) - 1;
+                hit[k] = valid && c < 27 && nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
+                key[k] = pair_cell_key(0u, nx, ny, nz);
+                hpos[k] = cell_hash(key[k]) & mask;
+            }
+#pragma unroll
+            for (int k = 0; k < kCellsPerLane; ++k)
+                if (hit[k]) raw[k] = __ldg(reinterpret_cast<const uint4*>(entries + hpos[k]));
+#pragma unroll
+            for (int k = 0; k < kCellsPerLane; ++k) {
+                if (!hit[k]) continue;
+                unsigned h = hpos[k];
+                unsigned long long kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
+                while (kk != key[k] && kk != kEmptyKey) {
+                    h = (h + 1) & mask;
+                    raw[k] = __ldg(reinterpret_cast<const uint4*>(entries + h));
+                    kk = ((unsigned long long)raw[k].y << 32) | raw[k].x;
+                }
+                hit[k] = kk == key[k];
+            }
+            // optimistic single pass: everything inside the radius
             int cnt = 0;
-            if (lane < 27) {
-                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-                if (nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536) {
-                    const unsigned long long key = pair_cell_key(0u, nx, ny, nz);
-                    const CellEntry e = grid_lookup(entries, mask, key);
-                    if (e.key == key) {
-                        off = e.off;
-                        cnt = (int)e.cnt;
+            double cum[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) cum[t] = 0.0;
+            fold_candidates(raw, hit, gpts, Px, Py, Pz,
+                            [&](unsigned long long b, int) { return b < r2bits; }, cnt, cum);
+            int inside = cnt;
+#pragma unroll
+            for (int o = 1; o < kGroup; o <<= 1) inside += __shfl_xor_sync(kFull, inside, o);
+            int k_used = inside;
+            if (inside > max_nn && inside <= kStage) {
+                // The cap binds (common on dense, close-range surfaces): keep exactly the max_nn nearest,
+                // ties by ascending index.  The group stages its in-radius candidates in shared memory and
+                // every lane ranks its share against all of them — K^2/8 compares on chip instead of a
+                // bisection that re-reads the candidates ~100 times.
+                k_used = max_nn;
+                int before = cnt;  // exclusive prefix of the per-lane in-radius counts inside the group
+#pragma unroll
+                for (int o = 1; o < kGroup; o <<= 1) {
+                    const int v = __shfl_up_sync(gmask, before, o, kGroup);
+                    if (g >= o) before += v;
+                }
+                before -= cnt;
+                {
+                    int w = before;
+#pragma unroll
+                    for (int k = 0; k < kCellsPerLane; ++k) {
+                        if (!hit[k]) continue;
+                        const unsigned off = raw[k].z;
+                        const int m = (int)raw[k].w;
+                        for (int j = 0; j < m; ++j) {
+                            const float4 t = __ldg(gpts + off + j);
+                            const unsigned long long b = (unsigned long long)__double_as_longlong(
+                                dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z));
+                            if (b < r2bits) {
+                                s_d2[gslot][w] = b;
+                                s_ip[gslot][w] = make_int2(__float_as_int(t.w), (int)(off + j));
+                                ++w;
+                            }
+                        }
                     }
                 }
-            }
-            int incl = cnt;
+                __syncwarp(gmask);
+                cnt = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int total = __shfl_sync(kFull, incl, 31);
-            const int excl = incl - cnt;
-
-            // pass 1: count neighbours inside the radius
-            int inside = 0;
-            for (int c0 = 0; c0 < total; c0 += 32) {
-                const int cnd = c0 + lane;
-                const int owner = warp_owner(incl, cnd);
-                const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-                const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-                bool in = false;
-                if (cnd < total) {
-                    const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                    in = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z) < r2;
+                for (int t = 0; t < 9; ++t) cum[t] = 0.0;
+                for (int e = g; e < inside; e += kGroup) {
+                    const unsigned long long be = s_d2[gslot][e];
+                    const int2 ie = s_ip[gslot][e];
+                    int rank = 0;
+                    for (int f = 0; f < inside; ++f) {
+                        const unsigned long long bf = s_d2[gslot][f];
+                        rank += (bf < be || (bf == be && s_ip[gslot][f].x < ie.x)) ? 1 : 0;
+                    }
+                    if (rank < max_nn) {
+                        const float4 t = __ldg(gpts + ie.y);
+                        const double x = t.x, y = t.y, z = t.z;
+                        ++cnt;
+                        cum[0] += x; cum[1] += y; cum[2] += z;
+                        cum[3] += x * x; cum[4] += x * y; cum[5] += x * z;
+                        cum[6] += y * y; cum[7] += y * z; cum[8] += z * z;
+                    }
                 }
-                inside += __popc(__ballot_sync(kFull, in));
-            }
-            // selection threshold: everything inside the radius, or the max_nn nearest
-            unsigned long long thr_bits = r2bits;  // admit d2 with bits < thr_bits ...
-            int tie_idx_max = -1;                  // ... plus d2 bits == thr_bits with idx <= tie_idx_max
-            int k_used = inside;
-            if (inside > max_nn) {
+                __syncwarp(gmask);
+            } else if (inside > max_nn) {
+                // more in-radius candidates than the staging area holds: exact max_nn-th nearest by
+                // bisection on the fp64 bit pattern.  Group-uniform, so the shuffles use the group mask.
                 k_used = max_nn;
                 unsigned long long lo = 0, hi = r2bits;
-                while (lo < hi) {  // smallest v with count(d2 <= v) >= max_nn
+                while (lo < hi) {  // smallest v with count(d2 <= v, d2 < r2) >= max_nn
                     const unsigned long long mid = lo + ((hi - lo) >> 1);
-                    int cle = 0;
-                    for (int c0 = 0; c0 < total; c0 += 32) {
-                        const int cnd = c0 + lane;
-                        const int owner = warp_owner(incl, cnd);
-                        const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-                        const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-                        bool le = false;
-                        if (cnd < total) {
-                            const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                            const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                            le = d2 < r2 && (unsigned long long)__double_as_longlong(d2) <= mid;
-                        }
-                        cle += __popc(__ballot_sync(kFull, le));
-                    }
+                    const int cle = group_sum(count_candidates(raw, hit, gpts, Px, Py, Pz,
+                                                               [&](unsigned long long b, int) { return b < r2bits && b <= mid; }),
+                                              gmask);
                     if (cle >= max_nn) hi = mid; else lo = mid + 1;
                 }
-                thr_bits = lo;
-                // ties at the threshold distance: admit the lowest indices until max_nn is reached
-                int clt = 0;
-                for (int c0 = 0; c0 < total; c0 += 32) {
-                    const int cnd = c0 + lane;
-                    const int owner = warp_owner(incl, cnd);
-                    const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-                    const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-                    bool lt = false;
-                    if (cnd < total) {
-                        const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                        const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                        lt = (unsigned long long)__double_as_longlong(d2) < thr_bits;
-                    }
-                    clt += __popc(__ballot_sync(kFull, lt));
-                }
+                const unsigned long long thr = lo;
+                const int clt = group_sum(count_candidates(raw, hit, gpts, Px, Py, Pz,
+                                                           [&](unsigned long long b, int) { return b < thr; }), gmask);
                 const int need = max_nn - clt;
                 int ilo = 0, ihi = 0x7ffffffe;
                 while (ilo < ihi) {  // smallest index bound admitting `need` ties
                     const int mid = ilo + ((ihi - ilo) >> 1);
-                    int ct = 0;
-                    for (int c0 = 0; c0 < total; c0 += 32) {
-                        const int cnd = c0 + lane;
-                        const int owner = warp_owner(incl, cnd);
-                        const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-                        const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-                        bool hit = false;
-                        if (cnd < total) {
-                            const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                            const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                            hit = (unsigned long long)__double_as_longlong(d2) == thr_bits && __float_as_int(t.w) <= mid;
-                        }
-                        ct += __popc(__ballot_sync(kFull, hit));
-                    }
+                    const int ct = group_sum(count_candidates(raw, hit, gpts, Px, Py, Pz,
+                                                              [&](unsigned long long b, int idx) { return b == thr && idx <= mid; }),
+                                             gmask);
                     if (ct >= need) ihi = mid; else ilo = mid + 1;
                 }
-                tie_idx_max = ilo;
+                const int tie_max = ilo;
+                cnt = 0;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) cum[t] = 0.0;
+                fold_candidates(raw, hit, gpts, Px, Py, Pz,
+                                [&](unsigned long long b, int idx) { return b < thr || (b == thr && idx <= tie_max); },
+                                cnt, cum);
             }
-            // pass 2: cumulants over the admitted neighbours
-            double cum[9];
+            // fold the group's cumulants (fixed butterfly order) and hand them to the lane that will
+            // solve this point: lane r*4 + gi
 #pragma unroll
-            for (int t = 0; t < 9; ++t) cum[t] = 0.0;
-            if (k_used >= 3) {
-                for (int c0 = 0; c0 < total; c0 += 32) {
-                    const int cnd = c0 + lane;
-                    const int owner = warp_owner(incl, cnd);
-                    const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-                    const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-                    if (cnd < total) {
-                        const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                        const double x = t.x, y = t.y, z = t.z;
-                        const double d2 = dist2_strict(Px, Py, Pz, x, y, z);
-                        const unsigned long long b = (unsigned long long)__double_as_longlong(d2);
-                        const bool take = inside > max_nn
-                                              ? (b < thr_bits || (b == thr_bits && __float_as_int(t.w) <= tie_idx_max))
-                                              : d2 < r2;
-                        if (take) {
-                            cum[0] += x; cum[1] += y; cum[2] += z;
-                            cum[3] += x * x; cum[4] += x * y; cum[5] += x * z;
-                            cum[6] += y * y; cum[7] += y * z; cum[8] += z * z;
-                        }
-                    }
-                }
+            for (int t = 0; t < 9; ++t) {
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-#pragma unroll
-                    for (int o = 16; o; o >>= 1) cum[t] += __shfl_xor_sync(kFull, cum[t], o);
-                }
+                for (int o = 1; o < kGroup; o <<= 1) cum[t] += __shfl_xor_sync(kFull, cum[t], o);
             }
-            if (lane == qi) {
+            const int src = (lane & 3) * kGroup;
+            const int kq = __shfl_sync(kFull, k_used, src);
 #pragma unroll
-                for (int t = 0; t < 9; ++t) mine[t] = cum[t];
-                mine_k = k_used;
+            for (int t = 0; t < 9; ++t) {
+                const double v = __shfl_sync(kFull, cum[t], src);
+                if ((lane >> 2) == r) mine[t] = v;
             }
+            if ((lane >> 2) == r) mine_k = kq;
         }
-        if (lane < qn) {
+        if (base + lane < n) {
             double nrm[3] = {0.0, 0.0, 1.0};
             if (mine_k >= 3) {
                 const double k = (double)mine_k;
