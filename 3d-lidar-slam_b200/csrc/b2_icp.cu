@@ -383,6 +383,17 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
     double best = INFINITY;
     int best_idx = 0x7fffffff;
     float bx = 0.f, by = 0.f, bz = 0.f;
+    // pair / slab grids: float32 screening state of this lane and the cells it resolved
+    const float Pxf = (float)Px, Pyf = (float)Py, Pzf = (float)Pz;
+    float bf = INFINITY, sf = INFINITY;
+    unsigned bpos = 0;
+    unsigned coff[kCellsPerLane + kProbeBatch];
+    int ccnt[kCellsPerLane + kProbeBatch];
+#pragma unroll
+    for (int k = 0; k < kCellsPerLane + kProbeBatch; ++k) {
+        coff[k] = 0;
+        ccnt[k] = 0;
+    }
     if (valid) {
 #pragma unroll
         for (int k0 = 0; k0 < kCellsPerLane; k0 += kProbeBatch) {
@@ -449,25 +460,57 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
                     if (kk != key[k]) continue;
                     const unsigned off = raw[k].z;
                     const int cnt = (int)raw[k].w;
-                    // candidates of a cell four at a time: the loads and the four distance chains are
-                    // independent (clamped index instead of predication), only the final compare/select
-                    // is sequential
-                    for (int j = 0; j < cnt; j += 4) {
-                        float4 t[4];
-                        double d2[4];
+                    coff[k0 + k] = off;
+                    ccnt[k0 + k] = cnt;
+                    // float32 screening pass over the cell's points (uniform, no fp64): keep this lane's
+                    // best and second-best float32 squared distance
+#pragma unroll 4
+                    for (int j = 0; j < cnt; ++j) {
+                        const float4 t = __ldg(a.gpts + off + j);
+                        const float fx = Pxf - t.x, fy = Pyf - t.y, fz = Pzf - t.z;
+                        const float d = fx * fx + fy * fy + fz * fz;
+                        if (d < bf) {
+                            sf = bf;
+                            bf = d;
+                            bpos = off + j;
+                        } else if (d < sf) {
+                            sf = d;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (KIND != 2) {
+        // Exact phase.  Let M bound |d2_f32 - d2| for every candidate (rounding of P to float32 plus the
+        // float32 arithmetic): every candidate's d2_f32 >= d2* - M, where d2* is the true minimum, so a
+        // candidate with d2_f32 > gmin + 2M has d2 > d2* and cannot be the nearest neighbour.  Only the
+        // contenders (normally one per group) are evaluated in fp64, in the strict order of the oracle.
+        float gmin = bf;
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) t[u] = __ldg(a.gpts + off + min(j + u, cnt - 1));
+        for (int o = 1; o < kGroup; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(kFull, gmin, o));
+        if (valid && gmin < INFINITY) {
+            const float e_abs = (fmaxf(fmaxf(fabsf(Pxf), fabsf(Pyf)), fabsf(Pzf)) + 4.0f * (float)meta.cell *
+                                                                                         (float)meta.brick + 1e-3f) * 1.2e-7f;
+            const float M = 3.5f * e_abs * sqrtf(gmin) + 3.0f * e_abs * e_abs + 1e-6f * gmin;
+            const float thr = (gmin + 2.0f * M) * 1.000002f + 1e-30f;
+            if (bf <= thr) {
+                if (sf > thr) {  // one contender in this lane
+                    const float4 t = __ldg(a.gpts + bpos);
+                    best = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
+                    best_idx = __float_as_int(t.w);
+                    bx = t.x; by = t.y; bz = t.z;
+                } else {  // several within the margin (near-ties): exact pass over this lane's cells
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            d2[u] = dist2_strict(Px, Py, Pz, (double)t[u].x, (double)t[u].y, (double)t[u].z);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int idx = __float_as_int(t[u].w);
-                            // a clamped duplicate re-offers the cell's last point: same (d2, idx), never wins twice
-                            if (d2[u] < best || (d2[u] == best && idx < best_idx)) {
-                                best = d2[u];
+                    for (int k = 0; k < kCellsPerLane; ++k) {
+                        for (int j = 0; j < ccnt[k]; ++j) {
+                            const float4 t = __ldg(a.gpts + coff[k] + j);
+                            const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
+                            const int idx = __float_as_int(t.w);
+                            if (d2 < best || (d2 == best && idx < best_idx)) {
+                                best = d2;
                                 best_idx = idx;
-                                bx = t[u].x; by = t[u].y; bz = t[u].z;
+                                bx = t.x; by = t.y; bz = t.z;
                             }
                         }
                     }
