@@ -20,6 +20,7 @@
 //
 // Algorithmic bytes of one launch: 16*Ns (queries) +
 // 16*sum_q cand(q) (candidate points) + 16*27*Ns (cell records) + 256*CTAs.
+#include <climits>
 #include <cstdlib>
 
 #include "b2_common.cuh"
@@ -371,6 +372,12 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
             cy = floor_div(cy, meta.brick);
             cz = floor_div(cz, meta.brick);
         }
+        // map grids: one range test per query instead of one per probe (a query outside the 2^21-cell
+        // key space cannot have a neighbour); poisoning cx makes every lane of the group skip the probes
+        if (KIND) {
+            const int lim = (1 << 20) - 2;
+            if (cx < -lim || cx > lim || cy < -lim || cy > lim || cz < -lim || cz > lim) cx = INT_MIN;
+        }
     }
     Px = __shfl_sync(kFull, Px, lead);
     Py = __shfl_sync(kFull, Py, lead);
@@ -394,7 +401,7 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
         coff[k] = 0;
         ccnt[k] = 0;
     }
-    if (valid) {
+    if (valid && cx != INT_MIN) {
 #pragma unroll
         for (int k0 = 0; k0 < kCellsPerLane; k0 += kProbeBatch) {
             unsigned long long key[kProbeBatch];
@@ -408,8 +415,7 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
                 const int nx = cx + c9 - 1, ny = cy + (c3 - 3 * c9) - 1, nz = cz + (c - 3 * c3) - 1;
                 const bool in_stencil = (k0 + k) < kCellsPerLane && c < 27;
                 if (KIND) {
-                    live[k] = in_stencil && nx > -(1 << 20) && nx < (1 << 20) && ny > -(1 << 20) && ny < (1 << 20) &&
-                              nz > -(1 << 20) && nz < (1 << 20);
+                    live[k] = in_stencil;
                     key[k] = map_cell_key(nx, ny, nz);
                 } else {
                     live[k] = in_stencil && nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
