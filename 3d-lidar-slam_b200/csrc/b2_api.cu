@@ -216,6 +216,13 @@ int b2_create(int device, b2_handle* out) {
         delete c;
         return B2_ERR_CUDA;
     }
+    if (icp_configure(c) != B2_OK) {
+        cudaFree(c->dev_status);
+        cudaFreeHost(c->host_mailbox);
+        cudaStreamDestroy(c->stream);
+        delete c;
+        return B2_ERR_CUDA;
+    }
     *out = reinterpret_cast<b2_handle>(c);
     return B2_OK;
 }

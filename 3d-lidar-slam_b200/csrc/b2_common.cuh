@@ -392,6 +392,7 @@ struct IcpParams {
 // results_dev[pair] is written when the pair finishes.  corr_out/d2_out (optional) receive the per-source
 // correspondence of the last evaluated transform.  search_only: one correspondence pass, no estimation.
 // check_every > 0: poll the finished-pair counter every that many launches (host sync) and stop early.
+int icp_configure(Context* c);
 int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, const int* ns_dev, int n_pairs,
             const GridView& grid, const float4* tgt_normals, const int* tgt_offsets, const double* init_dev,
             const IcpParams& prm, IcpResultDev* results_dev, int* corr_out, double* d2_out, int search_only,
