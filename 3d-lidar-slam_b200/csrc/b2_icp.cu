@@ -798,9 +798,17 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
     auto margin = [&](float d2f) -> float {  // bound of |d2_f32 - d2| for a candidate at float32 distance^2 d2f
         return 3.5f * e_abs * sqrtf(d2f) + 3.0f * e_abs * e_abs + 1e-6f * d2f;
     };
+    // keys are additive in the cell offsets while no field overflows: always for map keys (range-checked
+    // above), and for pair keys when the query's cell is not on the border of the 16-bit coordinate range
+    const bool interior = KIND || (cx >= 1 && cx <= 65534 && cy >= 1 && cy <= 65534 && cz >= 1 && cz <= 65534);
+    const unsigned long long kbase = KIND ? map_cell_key(cx - 1, cy - 1, cz - 1) : pair_cell_key(a.pair, cx - 1, cy - 1, cz - 1);
     auto key_of = [&](int code, bool& ok) -> unsigned long long {
+        if (interior) {
+            constexpr int sx = KIND ? 42 : 32, sy = KIND ? 21 : 16;
+            return kbase + ((unsigned long long)(code & 3) << sx) + ((unsigned long long)((code >> 2) & 3) << sy) +
+                   (unsigned long long)(code >> 4);
+        }
         const int nx = cx + (code & 3) - 1, ny = cy + ((code >> 2) & 3) - 1, nz = cz + (code >> 4) - 1;
-        if (KIND) return map_cell_key(nx, ny, nz);
         ok = nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
         return pair_cell_key(a.pair, nx, ny, nz);
     };
@@ -829,13 +837,9 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
             const float4 t = __ldg(cp + j);
             const float fx = Pxf - t.x, fy = Pyf - t.y, fz = Pzf - t.z;
             const float d = fx * fx + fy * fy + fz * fz;
-            if (d < bf) {
-                sf = bf;
-                bf = d;
-                bpos = raw.z + j;
-            } else if (d < sf) {
-                sf = d;
-            }
+            bpos = d < bf ? raw.z + j : bpos;
+            sf = fminf(sf, fmaxf(bf, d));  // second best of what has been seen
+            bf = fminf(bf, d);
         }
         if (bf < before) ub = fminf(ub, (bf + 2.0f * margin(bf)) * 1.00001f);  // true d2 of that point <= bf + M
     };
@@ -854,10 +858,15 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
         // This query's own list of neighbours that can still hold a closer point, nearest class first.  Every
         // lane walks ITS list, so a warp runs the max — not the union — over its lanes of the cells they need
         // (measured 10 % faster than a walk that is uniform over the warp, although that one coalesces better).
-        unsigned m = 0;
+        // (a face neighbour qualifies when its slab does; an edge or corner neighbour only if all its faces do)
+        const bool fxm = xm <= ub, fxp = xp <= ub, fym = ym <= ub, fyp = yp <= ub, fzm = zm <= ub, fzp = zp <= ub;
+        unsigned m = (fxm ? 1u << 1 : 0u) | (fxp ? 1u << 2 : 0u) | (fym ? 1u << 3 : 0u) | (fyp ? 1u << 4 : 0u) |
+                     (fzm ? 1u << 5 : 0u) | (fzp ? 1u << 6 : 0u);
+        if (((fxm || fxp) ? 1 : 0) + ((fym || fyp) ? 1 : 0) + ((fzm || fzp) ? 1 : 0) >= 2) {
 #pragma unroll
-        for (int b = 1; b < 27; ++b)
-            if (box_dist2(walk_code(b)) <= ub) m |= 1u << b;
+            for (int b = 7; b < 27; ++b)
+                if (box_dist2(walk_code(b)) <= ub) m |= 1u << b;
+        }
         while (m) {
             const int b = __ffs(m) - 1;
             m &= m - 1;
