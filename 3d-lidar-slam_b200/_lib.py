@@ -25,6 +25,7 @@ EXPORTS = [
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
+    "b2_set_icp_driver",
 ]
 
 
@@ -63,6 +64,7 @@ def load():
     lib.b2_version.restype = C.c_char_p
     lib.b2_last_error.restype = C.c_char_p
     lib.b2_last_error.argtypes = [vp]
+    lib.b2_set_icp_driver.argtypes = [vp, i32]
     lib.b2_launch_count.restype = C.c_ulonglong
     lib.b2_launch_count.argtypes = [vp]
     protos = {
@@ -181,6 +183,11 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.b2_synchronize(self.h))
+
+    def set_icp_driver(self, driver) -> None:
+        """'auto' | 'group' | 'sweep' (or 0/1/2): the kernel that runs ICP steps on pair / slab grids."""
+        code = {"auto": 0, "group": 1, "sweep": 2}.get(driver, driver)
+        self._check(self.lib.b2_set_icp_driver(self.h, int(code)))
 
     def launch_count(self) -> int:
         return int(self.lib.b2_launch_count(self.h))

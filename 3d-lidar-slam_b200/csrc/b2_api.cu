@@ -266,6 +266,14 @@ int b2_synchronize(b2_handle h) {
     return check_status(c);
 }
 
+int b2_set_icp_driver(b2_handle h, int driver) {
+    CTX(h);
+    if (driver < B2_ICP_DRIVER_AUTO || driver > B2_ICP_DRIVER_SWEEP)
+        return set_error(c, B2_ERR_INVALID, "b2_set_icp_driver: unknown driver %d", driver);
+    c->icp_driver = driver;
+    return B2_OK;
+}
+
 unsigned long long b2_launch_count(b2_handle h) {
     Context* c = reinterpret_cast<Context*>(h);
     return c ? c->launches : 0;

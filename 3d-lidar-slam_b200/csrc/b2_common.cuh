@@ -58,6 +58,7 @@ struct ScanGraph {
 };
 
 struct Context {
+    int icp_driver = 0;  // B2_ICP_DRIVER_*
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;

@@ -1351,10 +1351,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     if (!(prm.max_corr > 0.0)) return set_error(c, B2_ERR_INVALID, "max_correspondence_distance must be > 0");
     // Pair / slab grids have two drivers: the 4-lane-group kernel (parallel probes: best when the queries do
     // not fill the machine and latency is the cost) and the thread-per-query sweep (pruned walk: best when
-    // they do).  B2_ICP_DRIVER=group|sweep forces one (experiments).
-    static const char* driver_env = getenv("B2_ICP_DRIVER");
+    // they do).  b2_set_icp_driver forces one (parity tests run both; results are identical).
     bool sweep = grid.is_map != 2 && (long long)ns_max >= kSweepMinQueries;
-    if (driver_env && grid.is_map != 2) sweep = driver_env[0] == 's';
+    if (c->icp_driver != 0 && grid.is_map != 2) sweep = c->icp_driver == 2;
     const int gx = icp_grid_x(ns_max, n_pairs, sweep ? grid.is_map : 2);
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
     B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs);

@@ -68,6 +68,13 @@ int b2_set_stream(b2_handle h, void* cuda_stream); /* cudaStream_t; NULL = handl
 int b2_synchronize(b2_handle h);
 /* number of kernels this handle has launched so far (bench.py "gpu_launches") */
 unsigned long long b2_launch_count(b2_handle h);
+/* Which kernel runs the ICP step on pair / slab grids (results are identical; tests and tuning):
+ * B2_ICP_DRIVER_AUTO picks by problem size, _GROUP = 4 lanes per query (latency), _SWEEP = one thread
+ * per query with a pruned stencil walk (throughput).  Dense resident maps always use the group kernel. */
+#define B2_ICP_DRIVER_AUTO 0
+#define B2_ICP_DRIVER_GROUP 1
+#define B2_ICP_DRIVER_SWEEP 2
+int b2_set_icp_driver(b2_handle h, int driver);
 
 /* ---- layout helpers ----------------------------------------------------- */
 /* float32 [n,3] (host when src_on_host != 0, else device) -> float32 [n,4] device rows.

@@ -42,6 +42,15 @@ def engine(b2):
     eng.close()
 
 
+@pytest.fixture(params=["group", "sweep"])
+def driver(request, engine):
+    """Run a test under both ICP-step kernels of the pair / slab grids (include/b2slam.h B2_ICP_DRIVER_*):
+    the 4-lane-group kernel and the thread-per-query sweep must give identical results."""
+    engine.set_icp_driver(request.param)
+    yield request.param
+    engine.set_icp_driver("auto")
+
+
 @pytest.fixture(scope="session")
 def pair0():
     """Config-1-shaped pair (seed 0): float32 source / target scans and the true relative pose."""

@@ -93,7 +93,7 @@ def test_voxel_downsample_wide_key_range_retries(engine):
 
 
 # ------------------------------------------------------------------ correspondence search (A.3/A.4)
-def test_nn_search_bit_exact(engine, pair0):
+def test_nn_search_bit_exact(engine, pair0, driver):
     src, tgt, _ = pair0
     sd, _ = engine.voxel_downsample(engine.pack(src), 0.02)
     td, _ = engine.voxel_downsample(engine.pack(tgt), 0.02)
@@ -106,7 +106,7 @@ def test_nn_search_bit_exact(engine, pair0):
     assert (oidx >= 0).mean() > 0.5 and (oidx < 0).any()
 
 
-def test_nn_search_raw_scan_target_and_no_transform(engine, pair0):
+def test_nn_search_raw_scan_target_and_no_transform(engine, pair0, driver):
     src, tgt, _ = pair0
     idx, d2 = engine.nn_search(engine.pack(src[::3].copy()), engine.pack(tgt), 0.05)
     oidx, od2 = orc.nn_search(f64(src[::3]), f64(tgt), 0.05)
@@ -114,7 +114,7 @@ def test_nn_search_raw_scan_target_and_no_transform(engine, pair0):
     np.testing.assert_array_equal(d2.cpu().numpy(), od2)
 
 
-def test_nn_search_ties_strict_radius_and_misses(engine):
+def test_nn_search_ties_strict_radius_and_misses(engine, driver):
     tgt = np.array([[1, 0, 0], [-1, 0, 0], [0, 2, 0], [50, 50, 50]], dtype=np.float32)
     src = np.array([[0, 0, 0], [0, 1.5, 0], [20, 20, 20], [49.5, 50, 50]], dtype=np.float32)
     for radius in (1.5, 1.0, 0.6):
@@ -130,7 +130,7 @@ def _down(engine, a, v=0.02):
     return d
 
 
-def test_icp_point_to_point_config1(engine, b2, pair0):
+def test_icp_point_to_point_config1(engine, b2, pair0, driver):
     """BASELINE config 1: two 49k-pt scans, reference parameters, 30 iterations."""
     src, tgt, _ = pair0
     sd, td = _down(engine, src), _down(engine, tgt)
@@ -153,7 +153,7 @@ def test_icp_with_init_and_convergence_stop(engine, b2, pair0):
     assert_transform_close(res.matrix(), T_true, rad=1e-2, metres=2e-2)  # and it is near the true motion
 
 
-def test_icp_iteration_semantics(engine, b2, pair0):
+def test_icp_iteration_semantics(engine, b2, pair0, driver):
     src, tgt, _ = pair0
     sd, td = _down(engine, src), _down(engine, tgt)
     for it in (0, 1, 3):
@@ -164,7 +164,7 @@ def test_icp_iteration_semantics(engine, b2, pair0):
         np.testing.assert_allclose(res.matrix(), ores.transformation, atol=1e-12)
 
 
-def test_icp_no_overlap(engine, b2, pair0):
+def test_icp_no_overlap(engine, b2, pair0, driver):
     src, tgt, _ = pair0
     sd, td = _down(engine, src + np.float32(30.0)), _down(engine, tgt)
     res, corr = engine.icp(sd, td, b2.make_params(0.05, 30), want_corr=True)
@@ -173,7 +173,7 @@ def test_icp_no_overlap(engine, b2, pair0):
     assert (corr.cpu().numpy() == -1).all()
 
 
-def test_icp_point_to_plane_config3(engine, b2, pair0):
+def test_icp_point_to_plane_config3(engine, b2, pair0, driver):
     """BASELINE config 3: point-to-plane with on-GPU PCA normals (k = 20)."""
     src, tgt, T_true = pair0
     sd, td = _down(engine, src), _down(engine, tgt)
@@ -255,7 +255,7 @@ def test_map_fuse_export_matches_oracle(engine, pair0, voxel, max_corr):
     assert engine.map_size() == 0
 
 
-def test_map_icp_matches_oracle(engine, b2, pair0):
+def test_map_icp_matches_oracle(engine, b2, pair0, driver):
     src, tgt, _ = pair0
     origin = np.array([-9.0, -9.0, -9.0])
     for voxel in (0.05, 0.02):
@@ -309,7 +309,7 @@ def test_slam_sequence_resident_mode(engine, b2):
     np.testing.assert_allclose(engine.get_pose(), ref.pose, atol=1e-6)
 
 
-def test_batch_icp_matches_per_pair_oracle(engine, b2):
+def test_batch_icp_matches_per_pair_oracle(engine, b2, driver):
     from lidar_slam_b200 import synth
 
     pairs = [synth.make_pair(s) for s in (0, 1, 2)]
@@ -402,7 +402,7 @@ def test_select_points_preserves_order(engine):
     assert sel.shape[0] == kept
 
 
-def test_batch_icp_ragged_and_empty_pairs(engine, b2):
+def test_batch_icp_ragged_and_empty_pairs(engine, b2, driver):
     """Ragged batch: a full pair, a tiny pair, a pair with an EMPTY source and a non-overlapping pair."""
     from lidar_slam_b200 import synth
 
