@@ -25,7 +25,7 @@ EXPORTS = [
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
-    "b2_set_icp_driver",
+    "b2_set_icp_driver", "b2_ingest_pointcloud2",
 ]
 
 
@@ -75,6 +75,7 @@ def load():
         "b2_pack_xyz": [vp, vp, i32, i32, vp],
         "b2_unpack_xyz": [vp, vp, i32, vp, i32],
         "b2_project_pixels": [vp, vp, i32, f64, f64, f64, f64, i32, vp],
+        "b2_ingest_pointcloud2": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, pd, i32, vp, C.POINTER(C.c_int)],
         "b2_voxel_downsample": [vp, vp, i32, f64, pd, pd, vp, vp, C.POINTER(i32)],
         "b2_estimate_normals": [vp, vp, i32, f64, i32, vp],
         "b2_nn_search": [vp, vp, i32, vp, i32, pd, f64, vp, vp],
@@ -224,6 +225,38 @@ class Engine:
                                                out.data_ptr()))
         self.synchronize()
         return out
+
+    def ingest_pointcloud2(self, data, n_points: int, point_step: int = 12, offsets=(0, 4, 8),
+                           is_bigendian: bool = False, skip_nans: bool = True, intrinsics=None,
+                           numpy2: bool = False):
+        """PointCloud2 payload (bytes / bytearray / numpy uint8 on the host, or a CUDA uint8 tensor) ->
+        CUDA float32 [m,4] rows of the records without NaN, in order; with ``intrinsics=(fx, fy, cx, cy)``
+        the pixel->metric projection is applied in the same pass (b2_ingest_pointcloud2)."""
+        torch = self.torch
+        on_host = not (isinstance(data, torch.Tensor) and data.is_cuda)
+        if on_host:
+            if isinstance(data, torch.Tensor):
+                data = data.contiguous().numpy()
+            if isinstance(data, np.ndarray):
+                buf = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+            else:
+                buf = np.frombuffer(data, dtype=np.uint8)
+            nbytes, ptr = buf.size, (buf.ctypes.data if buf.size else None)
+        else:
+            buf = data.contiguous().view(torch.uint8).reshape(-1)
+            nbytes, ptr = buf.numel(), buf.data_ptr()
+        if nbytes < int(n_points) * int(point_step):
+            raise ValueError(f"payload of {nbytes} bytes is shorter than {n_points} x {point_step}")
+        out = self.empty_points(int(n_points))
+        k = (C.c_double * 4)(*[float(v) for v in intrinsics]) if intrinsics is not None else None
+        m = C.c_int(0)
+        self._check(self.lib.b2_ingest_pointcloud2(self.h, ptr, int(on_host), int(n_points), int(point_step),
+                                                   int(offsets[0]), int(offsets[1]), int(offsets[2]),
+                                                   int(is_bigendian), int(skip_nans), k, int(numpy2),
+                                                   out.data_ptr(), C.byref(m)))
+        if on_host:
+            self.synchronize()  # the staging copy reads the caller's buffer
+        return out[:m.value]
 
     # -- primitives ---------------------------------------------------------
     def voxel_downsample(self, pts, voxel: float, origin=None, T=None, want_keys: bool = True):

@@ -82,6 +82,43 @@ __global__ void project_kernel(const float* __restrict__ rec, int n, double fx, 
     out[i] = make_float4(x, y, z, 0.f);
 }
 
+// sensor_msgs_py.point_cloud2.read_points(msg, ("x","y","z"), skip_nans=True) (input_handler.py:65) for the
+// three float32 fields of a PointCloud2 byte buffer: one record per thread, byte-wise field assembly when a
+// field is not 4-byte aligned, optional byte swap, NaN flags for the order-preserving compaction that
+// follows, and (optionally) the pixel -> metric projection of generic_point_cloud_processor.py:93-108 fused in.
+template <bool ALIGNED>
+__global__ void ingest_kernel(const unsigned char* __restrict__ data, int n, int point_step, int off_x, int off_y,
+                              int off_z, int big_endian, int skip_nans, int project, double fx, double fy, double cx,
+                              double cy, int numpy2, float4* __restrict__ out, unsigned char* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* rec = data + (size_t)i * point_step;
+    auto field = [&](int off) -> float {
+        unsigned v;
+        if (ALIGNED) {
+            v = *reinterpret_cast<const unsigned*>(rec + off);
+        } else {
+            v = (unsigned)rec[off] | ((unsigned)rec[off + 1] << 8) | ((unsigned)rec[off + 2] << 16) |
+                ((unsigned)rec[off + 3] << 24);
+        }
+        if (big_endian) v = __byte_perm(v, 0, 0x0123);
+        return __uint_as_float(v);
+    };
+    const float xp = field(off_x), yp = field(off_y), z = field(off_z);
+    if (keep) keep[i] = (skip_nans && (isnan(xp) || isnan(yp) || isnan(z))) ? 0 : 1;
+    float x = xp, y = yp;
+    if (project) {
+        if (numpy2) {
+            x = __fdiv_rn(__fmul_rn(__fsub_rn(xp, (float)cx), z), (float)fx);
+            y = __fdiv_rn(__fmul_rn(__fsub_rn(yp, (float)cy), z), (float)fy);
+        } else {
+            x = (float)ddiv(dmul(dsub((double)xp, cx), (double)z), fx);
+            y = (float)ddiv(dmul(dsub((double)yp, cy), (double)z), fy);
+        }
+    }
+    out[i] = make_float4(x, y, z, 0.f);
+}
+
 __global__ void transform_kernel(const float4* __restrict__ in, int n, const double* __restrict__ T,
                                  float4* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -322,6 +359,60 @@ int b2_project_pixels(b2_handle h, const float* records_host, int n, double fx, 
     project_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, fx, fy, cx, cy, numpy2_semantics,
                                                                 (float4*)out_xyzw_dev);
     B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
+
+int b2_ingest_pointcloud2(b2_handle h, const void* data, int data_on_host, int n_points, int point_step, int off_x,
+                          int off_y, int off_z, int is_bigendian, int skip_nans, const double* intrinsics,
+                          int numpy2_semantics, float* out_xyzw_dev, int* n_out) {
+    CTX(h);
+    if (n_out) *n_out = 0;
+    if (n_points < 0 || (n_points > 0 && (!data || !out_xyzw_dev)))
+        return set_error(c, B2_ERR_INVALID, "b2_ingest_pointcloud2: bad arguments");
+    const int offs[3] = {off_x, off_y, off_z};
+    for (int k = 0; k < 3; ++k)
+        if (offs[k] < 0 || point_step < 12 || offs[k] + 4 > point_step)
+            return set_error(c, B2_ERR_INVALID, "b2_ingest_pointcloud2: field offset %d does not fit point_step %d",
+                             offs[k], point_step);
+    if (n_points == 0) return B2_OK;
+    const size_t bytes = (size_t)n_points * (size_t)point_step;
+    const unsigned char* raw = (const unsigned char*)data;
+    if (data_on_host) {
+        B2_WS(c, stage, unsigned char, WS_INGEST_RAW, bytes);
+        B2_CUDA_OK(c, cudaMemcpyAsync(stage, data, bytes, cudaMemcpyHostToDevice, c->stream));
+        raw = stage;
+    }
+    float4* dst = (float4*)out_xyzw_dev;
+    unsigned char* keep = nullptr;
+    if (skip_nans) {
+        B2_WS(c, tmp, float4, WS_INGEST_TMP, sizeof(float4) * (size_t)n_points);
+        B2_WS(c, kp, unsigned char, WS_INGEST_KEEP, (size_t)n_points);
+        dst = tmp;
+        keep = kp;
+    }
+    const double fx = intrinsics ? intrinsics[0] : 1.0, fy = intrinsics ? intrinsics[1] : 1.0;
+    const double cx = intrinsics ? intrinsics[2] : 0.0, cy = intrinsics ? intrinsics[3] : 0.0;
+    const bool aligned = point_step % 4 == 0 && off_x % 4 == 0 && off_y % 4 == 0 && off_z % 4 == 0 &&
+                         ((uintptr_t)raw % 4 == 0);
+    if (aligned)
+        ingest_kernel<true><<<div_up(n_points, kBlock), kBlock, 0, c->stream>>>(
+            raw, n_points, point_step, off_x, off_y, off_z, is_bigendian, skip_nans, intrinsics ? 1 : 0, fx, fy, cx, cy,
+            numpy2_semantics, dst, keep);
+    else
+        ingest_kernel<false><<<div_up(n_points, kBlock), kBlock, 0, c->stream>>>(
+            raw, n_points, point_step, off_x, off_y, off_z, is_bigendian, skip_nans, intrinsics ? 1 : 0, fx, fy, cx, cy,
+            numpy2_semantics, dst, keep);
+    B2_LAUNCH_CHECK(c);
+    if (!skip_nans) {
+        if (n_out) *n_out = n_points;
+        return B2_OK;
+    }
+    B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
+    B2_TRY(select_points(c, dst, n_points, keep, (float4*)out_xyzw_dev, cnt));
+    int* hn = (int*)c->host_mailbox + 724;
+    B2_CUDA_OK(c, cudaMemcpyAsync(hn, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    if (n_out) *n_out = *hn;
     return B2_OK;
 }
 

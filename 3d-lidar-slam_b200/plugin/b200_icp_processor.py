@@ -102,12 +102,27 @@ class B200ICPProcessor(ProcessPointClouds):
             rec = np.ascontiguousarray(_records_to_array(scan), dtype=np.float32)
             del scan
             pts4 = self._engine.project_pixels(rec, self.fx, self.fy, self.cx, self.cy, numpy2=self._numpy2)
-            self._map_cache = None
-            if self._mode == "resident":
-                self._construct_resident(None, pts4)
-            else:
-                self._construct_reference(pts4)
-            self.point_clouds_in_map += 1
+            self._register_device_scan(pts4)
+
+    def process_cloud(self, cloud) -> None:
+        """One scan given as the PointCloud2 it arrived in (``plugin.pointcloud2.PointCloud2``; the wire format
+        of input_handler.py:65-66): the payload bytes go to the device, where ``b2_ingest_pointcloud2`` does
+        what ``read_points(msg, ("x","y","z"), skip_nans=True)`` + ``project_pixel_to_3d`` do on the host in
+        the reference.  Same state changes as ``process()``; used for ROS-free replay (``plugin.bag``)."""
+        from . import pointcloud2 as pc2
+
+        self.logger.info(f"pcs processed so far: {self.point_clouds_in_map}")
+        pts4 = pc2.read_points_device(self._engine, cloud, ("x", "y", "z"), skip_nans=True,
+                                      intrinsics=(self.fx, self.fy, self.cx, self.cy), numpy2=self._numpy2)
+        self._register_device_scan(pts4)
+
+    def _register_device_scan(self, pts4) -> None:
+        self._map_cache = None
+        if self._mode == "resident":
+            self._construct_resident(None, pts4)
+        else:
+            self._construct_reference(pts4)
+        self.point_clouds_in_map += 1
 
     def construct_global_map(self, points: np.ndarray) -> None:
         """ICPProcessor.construct_global_map (icp_processor.py:43-75)."""

@@ -88,6 +88,16 @@ int b2_unpack_xyz(b2_handle h, const float* xyzw_dev, int n, float* out_xyz, int
  * numpy2_semantics != 0: float32 arithmetic (NEP 50); else float64 arithmetic rounded once. */
 int b2_project_pixels(b2_handle h, const float* records_host, int n, double fx, double fy, double cx, double cy,
                       int numpy2_semantics, float* out_xyzw_dev);
+/* sensor_msgs_py.point_cloud2.read_points(msg, field_names=("x","y","z"), skip_nans=True)
+ * (input_handler.py:65-66) on the raw PointCloud2 payload: n_points records of point_step bytes, the three
+ * float32 fields at byte offsets off_x/off_y/off_z (ARDepthViewController.swift:136-150 sends 12-byte
+ * records, offsets 0/4/8, little endian).  Records with a NaN in any of the three fields are dropped
+ * (skip_nans != 0), order preserved.  intrinsics != NULL ({fx, fy, cx, cy}): the pixel -> metric projection
+ * of b2_project_pixels is applied to the kept records in the same pass.  data may be host or device memory.
+ * out_xyzw_dev: float32 [n_points,4] device rows (first *n_out valid).  SURVEY.md section 8 row f3. */
+int b2_ingest_pointcloud2(b2_handle h, const void* data, int data_on_host, int n_points, int point_step, int off_x,
+                          int off_y, int off_z, int is_bigendian, int skip_nans, const double* intrinsics,
+                          int numpy2_semantics, float* out_xyzw_dev, int* n_out);
 
 /* ---- stateless primitives ----------------------------------------------- */
 /* PointCloud.voxel_down_sample(voxel) (icp_processor.py:90-91,132-133).
