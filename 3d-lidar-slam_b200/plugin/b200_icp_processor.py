@@ -95,9 +95,13 @@ class B200ICPProcessor(ProcessPointClouds):
         into the upload: the (x_px, y_px, depth) records go to the device as they are and
         ``b2_project_pixels`` back-projects them there, so the 49k-iteration Python loop of
         the reference — and any host-side array of metric points — disappears from the per-scan path."""
-        scan = self.data_transfer.pixel_depth_map_queue.get()
-        self.logger.debug(f"{len(scan)} points received from queue")
+        self.process_records(self.data_transfer.pixel_depth_map_queue.get())
+
+    def process_records(self, scan) -> None:
+        """The body of ``process()`` for a scan that has already been dequeued (``ProcessLoop`` drains the
+        input queue in batches)."""
         if scan is not None:
+            self.logger.debug(f"{len(scan)} points received from queue")
             self.logger.info(f"pcs processed so far: {self.point_clouds_in_map}")
             rec = np.ascontiguousarray(_records_to_array(scan), dtype=np.float32)
             del scan

@@ -163,3 +163,37 @@ def test_process_with_fused_projection_equals_host_projection():
     assert a.point_clouds_in_map == b.point_clouds_in_map == 4
     np.testing.assert_array_equal(a.previous_transformation[-1], b.previous_transformation[-1])
     np.testing.assert_array_equal(a.global_map, b.global_map)
+
+
+def test_process_loop_batches_scans_through_the_real_processor():
+    """ProcessLoop (row f4) drives the B200 processor: same poses and map as scan-by-scan process()."""
+    import threading
+    import time
+
+    from lidar_slam_b200 import synth
+    from lidar_slam_b200.plugin.process_pc_manager import ProcessLoop
+
+    scene = synth.make_corridor_scene(6, length=10.0)
+    poses = synth.corridor_trajectory(scene, 5, seed=6, step=0.02)
+    recs = [synth.scan_records(synth.render_depth(scene, p, seed=90 + k)).numpy() for k, p in enumerate(poses)]
+    a, dta = _processor(mode="resident", max_iteration=30, map_voxel=0.05)
+    b, dtb = _processor(mode="resident", max_iteration=30, map_voxel=0.05)
+    for r in recs:
+        dta.pixel_depth_map_queue.put(r)
+        dtb.pixel_depth_map_queue.put(r)
+    stop, reset = multiprocessing.Event(), multiprocessing.Event()
+    loop = ProcessLoop(a, dta, stop, reset, max_batch=4, idle_timeout=0.05)
+    th = threading.Thread(target=loop.run, daemon=True)
+    th.start()
+    for _ in recs:
+        b.process()
+    t0 = time.time()
+    while loop.scans_processed < len(recs) and time.time() - t0 < 60:
+        time.sleep(0.01)
+    stop.set()
+    th.join(timeout=10)
+    assert loop.scans_processed == len(recs) and loop.batches < len(recs)
+    np.testing.assert_array_equal(a.previous_transformation[-1], b.previous_transformation[-1])
+    published = dta.global_map_queue.get(timeout=5)
+    assert published.shape[1] == 3 and len(published) > 1000
+    np.testing.assert_array_equal(a.global_map, b.global_map)
