@@ -48,6 +48,15 @@ def main():
     cloud = eng.pack(np.concatenate([src.numpy(), tgt.numpy()]).astype(np.float32) + rng.normal(scale=1e-4, size=(98304, 3)).astype(np.float32))
     out["radius_outlier_98k_us"] = round(timed(eng, lambda: eng.radius_outlier_mask(cloud, 8, 0.023), reps=5), 1)
     out["statistical_outlier_98k_k45_us"] = round(timed(eng, lambda: eng.statistical_outlier_mask(cloud, 45, 3.5), reps=3, warm=1), 1)
+    # row f3: PointCloud2 payload (device-resident bytes) -> float4 rows, NaN records dropped, projection fused
+    k = synth.intrinsics()
+    for n, tag in ((49152, "49k"), (2_000_000, "2M")):
+        rec = np.stack([rng.integers(0, 256, n), rng.integers(0, 192, n), rng.uniform(0.3, 5.0, n)], axis=1).astype(np.float32)
+        rec[::97, 2] = np.nan
+        payload = torch.from_numpy(rec.view(np.uint8).reshape(-1)).cuda()
+        us = timed(eng, lambda: eng.ingest_pointcloud2(payload, n, 12, (0, 4, 8), intrinsics=k), reps=10)
+        out[f"ingest_pointcloud2_{tag}_us"] = round(us, 1)
+        out[f"ingest_pointcloud2_{tag}_GBps"] = round((12 * n + 16 * n + 16 * n + 16 * n) / us / 1e3, 1)  # payload + staged rows w/r + compacted rows
     print(json.dumps(out))
 
 
