@@ -770,8 +770,11 @@ struct SweepCfg {  // threads per sweep CTA (one CTA per SM): the register budge
 
 template <int MODE, int KIND>
 __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __restrict__ sT,
-                                           const double* __restrict__ sPivot, const GridMeta& meta, float4 p, int q,
-                                           double* __restrict__ acc) {
+                                           const double* __restrict__ sPivot, const GridMeta& meta, float4 p, bool valid,
+                                           int q, double* __restrict__ acc, unsigned long long* __restrict__ wbest,
+                                           unsigned* __restrict__ wsecond) {
+    // (warp-collective: all 32 lanes enter; `valid` marks the lanes that hold a query)
+    const int lane = threadIdx.x & 31;
     const D3 P = xform_strict(sT, (double)p.x, (double)p.y, (double)p.z);
     const double Px = P.x, Py = P.y, Pz = P.z;
     int cx = voxel_coord(Px, meta.origin[0], meta.cell);
@@ -782,10 +785,10 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
         cy = floor_div(cy, meta.brick);
         cz = floor_div(cz, meta.brick);
     }
-    bool searching = true;
+    bool searching = valid;
     if (KIND) {  // a query outside the 2^21-cell key space of a map cannot have a neighbour
         const int lim = (1 << 20) - 2;
-        searching = !(cx < -lim || cx > lim || cy < -lim || cy > lim || cz < -lim || cz > lim);
+        searching = searching && !(cx < -lim || cx > lim || cy < -lim || cy > lim || cz < -lim || cz > lim);
     }
     const double Ed = KIND == 1 ? meta.cell * (double)meta.brick : meta.cell;
     const float E = (float)Ed;
@@ -802,25 +805,18 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
     // above), and for pair keys when the query's cell is not on the border of the 16-bit coordinate range
     const bool interior = KIND || (cx >= 1 && cx <= 65534 && cy >= 1 && cy <= 65534 && cz >= 1 && cz <= 65534);
     const unsigned long long kbase = KIND ? map_cell_key(cx - 1, cy - 1, cz - 1) : pair_cell_key(a.pair, cx - 1, cy - 1, cz - 1);
+    auto key_delta = [](int code) -> unsigned long long {
+        constexpr int sx = KIND ? 42 : 32, sy = KIND ? 21 : 16;
+        return ((unsigned long long)(code & 3) << sx) + ((unsigned long long)((code >> 2) & 3) << sy) +
+               (unsigned long long)(code >> 4);
+    };
     auto key_of = [&](int code, bool& ok) -> unsigned long long {
-        if (interior) {
-            constexpr int sx = KIND ? 42 : 32, sy = KIND ? 21 : 16;
-            return kbase + ((unsigned long long)(code & 3) << sx) + ((unsigned long long)((code >> 2) & 3) << sy) +
-                   (unsigned long long)(code >> 4);
-        }
+        if (interior) return kbase + key_delta(code);
         const int nx = cx + (code & 3) - 1, ny = cy + ((code >> 2) & 3) - 1, nz = cz + (code >> 4) - 1;
         ok = nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
         return pair_cell_key(a.pair, nx, ny, nz);
     };
-
-    float bf = INFINITY, sf = INFINITY;  // best / second-best float32 squared distance
-    unsigned bpos = 0;
-    float ub = (float)a.r2 * 1.00001f;  // nothing at or beyond the radius can be a correspondence
-    // probe one cell and screen its points; tighten the bound when the best improved
-    auto visit = [&](int code) {
-        bool ok = true;
-        const unsigned long long key = key_of(code, ok);
-        if (!ok) return;
+    auto probe = [&](unsigned long long key, unsigned& off, int& cnt) -> bool {  // is the cell occupied?
         unsigned h = cell_hash(key) & a.mask;
         uint4 raw = __ldg(reinterpret_cast<const uint4*>(a.entries + h));
         unsigned long long kk = ((unsigned long long)raw.y << 32) | raw.x;
@@ -829,52 +825,130 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
             raw = __ldg(reinterpret_cast<const uint4*>(a.entries + h));
             kk = ((unsigned long long)raw.y << 32) | raw.x;
         }
-        if (kk != key) return;
-        const float4* cp = a.gpts + raw.z;
-        const int cnt = (int)raw.w;
-        const float before = bf;
+        off = raw.z;
+        cnt = (int)raw.w;
+        return kk == key;
+    };
+
+    float bf = INFINITY, sf = INFINITY;  // best / second-best float32 squared distance
+    unsigned bpos = 0;
+    float ub = (float)a.r2 * 1.00001f;  // nothing at or beyond the radius can be a correspondence
+    // float32 screening of the points [off, off + cnt) for a query at (x, y, z): running best two
+    auto screen_cell = [&](unsigned off, int cnt, float x, float y, float z, float& b1, float& b2, unsigned& bp) {
+        const float4* cp = a.gpts + off;
         for (int j = 0; j < cnt; ++j) {
             const float4 t = __ldg(cp + j);
-            const float fx = Pxf - t.x, fy = Pyf - t.y, fz = Pzf - t.z;
+            const float fx = x - t.x, fy = y - t.y, fz = z - t.z;
             const float d = fx * fx + fy * fy + fz * fz;
-            bpos = d < bf ? raw.z + j : bpos;
-            sf = fminf(sf, fmaxf(bf, d));  // second best of what has been seen
-            bf = fminf(bf, d);
+            bp = d < b1 ? off + j : bp;
+            b2 = fminf(b2, fmaxf(b1, d));  // second best of what has been seen
+            b1 = fminf(b1, d);
         }
-        if (bf < before) ub = fminf(ub, (bf + 2.0f * margin(bf)) * 1.00001f);  // true d2 of that point <= bf + M
     };
+    unsigned m = 0;  // this query's list: bit b = walk position b can still hold a closer point
+    float xm = 0.f, xp = 0.f, ym = 0.f, yp = 0.f, zm = 0.f, zp = 0.f;
     if (searching) {
-        visit(offset_code(0, 0, 0));
+        {  // the query's own cell first: it usually holds the neighbour and gives the bound for the rest
+            bool ok = true;
+            const unsigned long long key = key_of(offset_code(0, 0, 0), ok);
+            unsigned off;
+            int cnt;
+            if (ok && probe(key, off, cnt)) {
+                screen_cell(off, cnt, Pxf, Pyf, Pzf, bf, sf, bpos);
+                if (bf < INFINITY) ub = fminf(ub, (bf + 2.0f * margin(bf)) * 1.00001f);  // true d2 <= bf + M
+            }
+        }
         // conservative (too small) squared distance from the query to the slab of cells at -1 / +1 per axis
         auto sq = [](float v) { return v * v * 0.9999f; };
-        const float xm = sq(fmaxf(ax - slack, 0.f)), xp = sq(fmaxf(E - ax - slack, 0.f));
-        const float ym = sq(fmaxf(ay - slack, 0.f)), yp = sq(fmaxf(E - ay - slack, 0.f));
-        const float zm = sq(fmaxf(az - slack, 0.f)), zp = sq(fmaxf(E - az - slack, 0.f));
-        auto box_dist2 = [&](int code) -> float {
-            const int dx = (code & 3) - 1, dy = ((code >> 2) & 3) - 1, dz = (code >> 4) - 1;
-            return (dx < 0 ? xm : (dx > 0 ? xp : 0.f)) + (dy < 0 ? ym : (dy > 0 ? yp : 0.f)) +
-                   (dz < 0 ? zm : (dz > 0 ? zp : 0.f));
-        };
-        // This query's own list of neighbours that can still hold a closer point, nearest class first.  Every
-        // lane walks ITS list, so a warp runs the max — not the union — over its lanes of the cells they need
-        // (measured 10 % faster than a walk that is uniform over the warp, although that one coalesces better).
+        xm = sq(fmaxf(ax - slack, 0.f)); xp = sq(fmaxf(E - ax - slack, 0.f));
+        ym = sq(fmaxf(ay - slack, 0.f)); yp = sq(fmaxf(E - ay - slack, 0.f));
+        zm = sq(fmaxf(az - slack, 0.f)); zp = sq(fmaxf(E - az - slack, 0.f));
         // (a face neighbour qualifies when its slab does; an edge or corner neighbour only if all its faces do)
         const bool fxm = xm <= ub, fxp = xp <= ub, fym = ym <= ub, fyp = yp <= ub, fzm = zm <= ub, fzp = zp <= ub;
-        unsigned m = (fxm ? 1u << 1 : 0u) | (fxp ? 1u << 2 : 0u) | (fym ? 1u << 3 : 0u) | (fyp ? 1u << 4 : 0u) |
-                     (fzm ? 1u << 5 : 0u) | (fzp ? 1u << 6 : 0u);
+        m = (fxm ? 1u << 1 : 0u) | (fxp ? 1u << 2 : 0u) | (fym ? 1u << 3 : 0u) | (fyp ? 1u << 4 : 0u) |
+            (fzm ? 1u << 5 : 0u) | (fzp ? 1u << 6 : 0u);
         if (((fxm || fxp) ? 1 : 0) + ((fym || fyp) ? 1 : 0) + ((fzm || fzp) ? 1 : 0) >= 2) {
 #pragma unroll
-            for (int b = 7; b < 27; ++b)
-                if (box_dist2(walk_code(b)) <= ub) m |= 1u << b;
-        }
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int code = a.walk[b];
-            if (box_dist2(code) > ub) continue;  // the bound tightened since the list was built
-            visit(code);
+            for (int b = 7; b < 27; ++b) {
+                const int code = walk_code(b), dx = (code & 3) - 1, dy = ((code >> 2) & 3) - 1, dz = (code >> 4) - 1;
+                const float lb = (dx < 0 ? xm : (dx > 0 ? xp : 0.f)) + (dy < 0 ? ym : (dy > 0 ? yp : 0.f)) +
+                                 (dz < 0 ? zm : (dz > 0 ? zp : 0.f));
+                if (lb <= ub) m |= 1u << b;
+            }
         }
     }
+    // ---- the neighbour cells, pooled over the warp ---------------------------------------------------
+    // List lengths are very uneven (most queries need 1-3 neighbours, a query without a close point needs
+    // all 26), and a warp that walks per lane waits for its longest list.  So the (query, cell) pairs of the
+    // whole warp form one pool of tasks, 32 at a time: a lane takes a task, fetches the owner's key base and
+    // coordinates by shuffle, probes the cell, screens its points and merges its best two into the owner's
+    // slot in shared memory (an atomic min on (d2, position) keeps the best; whatever loses goes to the
+    // second best).  The float32 arithmetic is the owner's, so the result does not depend on who computed it.
+    const unsigned mp = interior ? m : 0u;  // (border cells of the 16-bit pair key space: walked by the owner below)
+    const int c_own = __popc(mp);
+    int pre = c_own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, pre, o);
+        if (lane >= o) pre += v;
+    }
+    const int total = __shfl_sync(kFull, pre, 31);
+    pre -= c_own;  // exclusive prefix: first task of this lane
+    wbest[lane] = ((unsigned long long)__float_as_uint(bf) << 32) | bpos;
+    wsecond[lane] = __float_as_uint(sf);
+    __syncwarp();
+    for (int g0 = 0; g0 < total; g0 += 32) {  // warp-uniform trip count
+        const int g = g0 + lane;
+        int o = 0;  // owner: the last lane whose first task is <= g
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+            const int cand = o + step;
+            const int pv = __shfl_sync(kFull, pre, cand & 31);
+            if (cand < 32 && pv <= g) o = cand;
+        }
+        const int opre = __shfl_sync(kFull, pre, o);
+        const unsigned om = __shfl_sync(kFull, mp, o);
+        const unsigned long long okb = __shfl_sync(kFull, kbase, o);
+        const float ox = __shfl_sync(kFull, Pxf, o), oy = __shfl_sync(kFull, Pyf, o), oz = __shfl_sync(kFull, Pzf, o);
+        if (g < total) {
+            const int b = __fns(om, 0, g - opre + 1);  // the (g - opre)-th cell of the owner's list
+            unsigned off;
+            int cnt;
+            if (probe(okb + key_delta(a.walk[b]), off, cnt)) {
+                float l1 = INFINITY, l2 = INFINITY;
+                unsigned lp = 0;
+                screen_cell(off, cnt, ox, oy, oz, l1, l2, lp);
+                if (l1 < INFINITY) {
+                    const unsigned long long mine = ((unsigned long long)__float_as_uint(l1) << 32) | lp;
+                    const unsigned long long old = atomicMin(wbest + o, mine);
+                    // non-negative floats order like their bit patterns
+                    const unsigned loser = mine < old ? (unsigned)(old >> 32) : __float_as_uint(l1);
+                    atomicMin(wsecond + o, min(loser, __float_as_uint(l2)));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (mp) {
+        const unsigned long long w = wbest[lane];
+        bf = __uint_as_float((unsigned)(w >> 32));
+        bpos = (unsigned)w;
+        sf = __uint_as_float(wsecond[lane]);
+    }
+    __syncwarp();  // the slots are reused by the warp's next round
+    if (!interior && m) {  // rare: per-lane walk with range-checked keys
+        unsigned mm = m;
+        while (mm) {
+            const int b = __ffs(mm) - 1;
+            mm &= mm - 1;
+            bool ok = true;
+            const unsigned long long key = key_of(a.walk[b], ok);
+            unsigned off;
+            int cnt;
+            if (ok && probe(key, off, cnt)) screen_cell(off, cnt, Pxf, Pyf, Pzf, bf, sf, bpos);
+        }
+    }
+    if (!valid) return;
     // Exact phase.  Let M bound |d2_f32 - d2| for every candidate (rounding of P to float32 plus the float32
     // arithmetic): every candidate's d2_f32 >= d2* - M, where d2* is the true minimum, so a candidate with
     // d2_f32 > bf + 2M has d2 > d2* and cannot be the nearest neighbour.
@@ -959,6 +1033,8 @@ icp_sweep_kernel(const float4* __restrict__ src, const int* __restrict__ src_off
     IcpState* st = states + pair;
     extern __shared__ double sAcc[];  // [NT][kT]: one accumulator column per thread
     __shared__ unsigned char sWalk[32];
+    __shared__ unsigned long long sBest[SweepCfg<MODE>::kT];  // per warp: 32 slots of (best d2 bits, position)
+    __shared__ unsigned sSecond[SweepCfg<MODE>::kT];          //           and of the second-best d2 bits
     __shared__ IcpState sState;
     __shared__ GridMeta sMeta;
     __shared__ double sRed[kThreads / 32][kTerms];
@@ -1000,7 +1076,10 @@ icp_sweep_kernel(const float4* __restrict__ src, const int* __restrict__ src_off
     const int warps_total = gridDim.x * (kT / 32);
     for (int blk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; sb + blk * 32 < se; blk += warps_total) {
         const int q = sb + blk * 32 + lane;
-        if (q < se) search_one<MODE, KIND>(a, sState.T, sState.pivot, sMeta, __ldg(src + q), q, sAcc + threadIdx.x);
+        const bool valid = q < se;
+        const float4 p = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        search_one<MODE, KIND>(a, sState.T, sState.pivot, sMeta, p, valid, q, sAcc + threadIdx.x,
+                               sBest + (threadIdx.x & ~31), sSecond + (threadIdx.x & ~31));
     }
     if (search_only) return;
 
