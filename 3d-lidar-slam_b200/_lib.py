@@ -25,7 +25,7 @@ EXPORTS = [
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
-    "b2_set_icp_driver", "b2_ingest_pointcloud2",
+    "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results",
 ]
 
 
@@ -89,6 +89,7 @@ def load():
         "b2_map_icp": [vp, vp, i32, pd, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan_dev": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
+        "b2_slam_results": [vp, i32, C.POINTER(IcpResult)],
         "b2_map_stencil_candidates": [vp, vp, i32, pd, C.POINTER(i64)],
         "b2_radius_outlier_mask": [vp, vp, i32, i32, f64, vp, C.POINTER(i32)],
         "b2_statistical_outlier_mask": [vp, vp, i32, i32, f64, f64, vp, C.POINTER(i32)],
@@ -371,7 +372,9 @@ class Engine:
         return res
 
     def slam_scan(self, xyz_host: np.ndarray, ds_voxel: float, params: IcpParams, want_result: bool = True):
-        """xyz_host: float32 [n,3] C-contiguous host array (pinned for best H2D speed)."""
+        """xyz_host: float32 [n,3] C-contiguous host array (pinned for best H2D speed).  With
+        ``want_result=False`` the call only enqueues work (a pinned array must then stay alive until the next
+        synchronising call); fetch the poses later with ``slam_results``."""
         if xyz_host.dtype != np.float32 or xyz_host.ndim != 2 or xyz_host.shape[1] != 3 or \
                 not xyz_host.flags["C_CONTIGUOUS"]:
             raise ValueError("expected a C-contiguous float32 [n,3] host array")
@@ -388,6 +391,13 @@ class Engine:
         self._check(self.lib.b2_slam_scan_dev(self.h, scan4.data_ptr(), scan4.shape[0], float(ds_voxel),
                                               C.byref(params), C.byref(res) if want_result else None))
         return res
+
+    def slam_results(self, count: int):
+        """Results of the last ``count`` scans submitted with ``want_result=False``, oldest first (one stream
+        synchronisation for the whole batch)."""
+        arr = (IcpResult * int(count))()
+        self._check(self.lib.b2_slam_results(self.h, int(count), arr))
+        return list(arr)
 
     def stencil_candidates(self, src, T=None, tgt=None, cell: float = 0.0) -> int:
         """Points under the 27-cell stencils of the (transformed) source: against the resident map, or

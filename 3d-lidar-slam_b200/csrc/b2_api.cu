@@ -253,7 +253,16 @@ int b2_create(int device, b2_handle* out) {
         delete c;
         return B2_ERR_CUDA;
     }
-    if (icp_configure(c) != B2_OK) {
+    bool aux_ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaHostAlloc(&c->result_ring, sizeof(IcpResultDev) * kResultRing, cudaHostAllocDefault) == cudaSuccess;
+    for (int i = 0; i < 2 && aux_ok; ++i)
+        aux_ok = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
+    c->ring_first = new unsigned char[kResultRing]();
+    if (!aux_ok || icp_configure(c) != B2_OK) {
+        delete[] c->ring_first;
+        if (c->result_ring) cudaFreeHost(c->result_ring);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         cudaFree(c->dev_status);
         cudaFreeHost(c->host_mailbox);
         cudaStreamDestroy(c->stream);
@@ -273,6 +282,14 @@ int b2_destroy(b2_handle h) {
         if (b.p) cudaFree(b.p);
     cudaFree(c->dev_status);
     cudaFreeHost(c->host_mailbox);
+    cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(c->ev_copied[i]);
+        cudaEventDestroy(c->ev_consumed[i]);
+    }
+    cudaStreamDestroy(c->copy_stream);
+    cudaFreeHost(c->result_ring);
+    delete[] c->ring_first;
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return B2_OK;
@@ -798,15 +815,33 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
     if (scan_dev) {
         B2_CUDA_OK(c, cudaMemcpyAsync(scan, scan_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     } else {
-        B2_WS(c, stage, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)cap);
-        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+        // upload on the copy stream into the staging buffer that is not being unpacked: with a caller that
+        // runs ahead (out == NULL) the copy of this scan overlaps the registration of the previous one
+        const int sb = (int)(c->scan_seq & 1u);
+        B2_WS(c, stage0, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)cap);
+        B2_WS(c, stage1, float, WS_STAGE_XYZ2, sizeof(float) * 3 * (size_t)cap);
+        float* stage = sb ? stage1 : stage0;
+        if (c->consumed_valid[sb]) B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[sb], 0));
+        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+        B2_CUDA_OK(c, cudaEventRecord(c->ev_copied[sb], c->copy_stream));
+        B2_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[sb], 0));
         pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);
         B2_LAUNCH_CHECK(c);
+        B2_CUDA_OK(c, cudaEventRecord(c->ev_consumed[sb], c->stream));
+        c->consumed_valid[sb] = true;
     }
     if (map_empty) B2_TRY(slam_body(c, scan, cap, n_dev, ds_voxel, params, true));
     else B2_TRY(slam_body_graphed(c, scan, cap, n_dev, ds_voxel, params));
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
+    {   // every scan leaves its result in the pinned ring (asynchronous copy): b2_slam_results reads it later
+        const int slot = (int)(c->scans_total % kResultRing);
+        IcpResultDev* rr = (IcpResultDev*)c->result_ring + slot;
+        c->ring_first[slot] = map_empty ? 1 : 0;
+        if (map_empty) B2_CUDA_OK(c, cudaMemcpyAsync(rr->T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
+        else B2_CUDA_OK(c, cudaMemcpyAsync(rr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+        c->scans_total++;
+    }
     if (out) {
         IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
         if (map_empty) {
@@ -840,6 +875,22 @@ int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, con
                  b2_icp_result* out) {
     CTX(h);
     return slam_scan_entry(c, xyz_host, nullptr, n, ds_voxel, params, out);
+}
+
+int b2_slam_results(b2_handle h, int count, b2_icp_result* out) {
+    CTX(h);
+    if (count < 0 || (count > 0 && !out)) return set_error(c, B2_ERR_INVALID, "b2_slam_results: bad arguments");
+    if ((unsigned long long)count > c->scans_total || count > kResultRing)
+        return set_error(c, B2_ERR_INVALID, "b2_slam_results: %d results asked, %llu scans registered, ring of %d",
+                         count, c->scans_total, kResultRing);
+    B2_TRY(check_status(c));  // waits for the stream: every pending result has landed in the ring
+    for (int i = 0; i < count; ++i) {
+        const int slot = (int)((c->scans_total - (unsigned long long)count + i) % kResultRing);
+        IcpResultDev r = ((const IcpResultDev*)c->result_ring)[slot];
+        if (c->ring_first[slot]) { r.fitness = 0.0; r.rmse = 0.0; r.iterations = 0; r.n_corr = 0; }
+        fill_result(&r, out + i);
+    }
+    return B2_OK;
 }
 
 int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_voxel, const b2_icp_params* params,

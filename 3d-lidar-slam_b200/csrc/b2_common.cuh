@@ -42,7 +42,7 @@ enum WsSlot : int {
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
     WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_SCAN_COUNT, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D,
-    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_NUM_SLOTS
+    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu
@@ -74,7 +74,17 @@ struct Context {
     bool capturing = false;                // inside stream capture: no allocation, no synchronisation
     unsigned scan_seq = 0;                 // scans submitted (indexes the pinned count ring)
     ScanGraph scan_graph;
+    // b2_slam_scan with host scans: uploads run on a second stream into two alternating staging buffers, so
+    // the copy of scan k+1 overlaps the registration of scan k
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool consumed_valid[2] = {false, false};
+    // deferred read-back (b2_slam_scan with out == NULL, then b2_slam_results): pinned ring of per-scan results
+    void* result_ring = nullptr;
+    unsigned char* ring_first = nullptr;   // slot holds a first-scan record (pose only)
+    unsigned long long scans_total = 0;
 };
+constexpr int kResultRing = 1024;
 
 int set_error(Context* c, int code, const char* fmt, ...);
 void* ws_get(Context* c, int slot, size_t bytes);  // nullptr on failure (error set)

@@ -40,6 +40,11 @@ def main():
     out["icp_p2p_pair_30it_us"] = round(timed(eng, lambda: eng.icp(sd, td, p30)), 1)
     p30l = b2.make_params(0.05, 30, mode=b2.P2L, rel_fitness=0.0, rel_rmse=0.0)
     out["icp_p2l_pair_30it_us"] = round(timed(eng, lambda: eng.icp(sd, td, p30l, tgt_normals=nrm)), 1)
+    eng.set_icp_driver("sweep")  # the batch driver forced onto a single pair (auto picks the group kernel here)
+    out["icp_p2p_pair_30it_sweep_us"] = round(timed(eng, lambda: eng.icp(sd, td, p30)), 1)
+    out["icp_p2l_pair_30it_sweep_us"] = round(timed(eng, lambda: eng.icp(sd, td, p30l, tgt_normals=nrm)), 1)
+    out["nn_search_29k_vs_29k_sweep_us"] = round(timed(eng, lambda: eng.nn_search(sd, td, 0.05)), 1)
+    eng.set_icp_driver("auto")
     out["transform_49k_us"] = round(timed(eng, lambda: eng.transform(s4, T)), 1)
     eng.map_init(0.05, [-9.0, -9.0, -9.0], 0.05, 1 << 20)
     eng.map_fuse(t4)

@@ -176,6 +176,11 @@ int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, con
  * device-resident batches): no upload, otherwise identical. */
 int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_voxel, const b2_icp_params* params,
                      b2_icp_result* out);
+/* Deferred read-back for callers that submit scans faster than they need the poses: pass out == NULL to
+ * b2_slam_scan / b2_slam_scan_dev (the call then only enqueues work; a pinned host scan must stay valid
+ * until the next synchronising call) and collect the results of the last `count` scans here, oldest
+ * first (one stream synchronisation for the whole batch; at most 1024 results are kept). */
+int b2_slam_results(b2_handle h, int count, b2_icp_result* out);
 /* Number of resident-map points inside the 27-cell stencils of the transformed source points —
  * the data-dependent term of the search's algorithmic-byte model. */
 int b2_map_stencil_candidates(b2_handle h, const float* src_dev, int ns, const double* T, long long* n_candidates);

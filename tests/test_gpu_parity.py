@@ -449,3 +449,35 @@ def test_slam_sequence_with_varying_scan_sizes(engine, b2):
         assert res.n_correspondences == int((ores.correspondence >= 0).sum())
         assert_transform_close(res.matrix(), ores.transformation)
     assert len(set(sizes)) == len(sizes) and max(sizes) < 30000
+
+
+def test_deferred_results_equal_per_scan_results(engine, b2):
+    """b2_slam_scan with out == NULL + b2_slam_results (uploads double-buffered on the copy stream) gives, scan
+    for scan, exactly what the synchronous call returns."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(11, length=10.0)
+    poses = synth.corridor_trajectory(scene, 7, seed=11, step=0.02)
+    scans = [np.ascontiguousarray(synth.render_scan(scene, p, seed=70 + k).numpy()) for k, p in enumerate(poses)]
+    prm = b2.make_params(0.05, 30)
+    origin = np.array([-20.0, -20.0, -20.0])
+    engine.map_init(0.05, origin, 0.05, 1 << 18)
+    sync = [engine.slam_scan(s, 0.02, prm) for s in scans]
+    map_a, _ = engine.map_export()
+    map_a = map_a.clone()
+    engine.map_init(0.05, origin, 0.05, 1 << 18)
+    engine.set_pose(np.eye(4))
+    pinned = [torch.from_numpy(s).pin_memory() for s in scans]  # truly asynchronous uploads
+    for p in pinned:
+        assert engine.slam_scan(p.numpy(), 0.02, prm, want_result=False) is None
+    got = engine.slam_results(len(scans))
+    for a, b in zip(sync, got):
+        np.testing.assert_array_equal(a.matrix(), b.matrix())
+        assert (a.fitness, a.inlier_rmse, a.iterations, a.n_correspondences) == \
+               (b.fitness, b.inlier_rmse, b.iterations, b.n_correspondences)
+    assert got[0].iterations == 0 and got[0].fitness == 0.0  # the first scan becomes the map
+    map_b, _ = engine.map_export()
+    assert torch.equal(map_a, map_b)
+    assert [r.iterations for r in engine.slam_results(3)] == [r.iterations for r in sync[-3:]]
+    with pytest.raises(b2.B2Error, match="results asked"):
+        engine.slam_results(100000)
