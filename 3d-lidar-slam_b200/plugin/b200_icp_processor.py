@@ -45,6 +45,8 @@ class B200ICPProcessor(ProcessPointClouds):
         if maintenance not in ("voxel", "off", "full"):
             raise ValueError(f"unknown maintenance {maintenance!r}")
         self._map_cache = None
+        self._defer = False
+        self._pending_first = []   # one flag per deferred scan: was it the first scan of the map?
         self._mode = mode
         self._engine = _lib.Engine(device)  # raises without CUDA / without the built library
         self._voxel = float(voxel_size)
@@ -97,9 +99,32 @@ class B200ICPProcessor(ProcessPointClouds):
         the reference — and any host-side array of metric points — disappears from the per-scan path."""
         self.process_records(self.data_transfer.pixel_depth_map_queue.get())
 
-    def process_records(self, scan) -> None:
+    def process_records(self, scan, defer_result: bool = False) -> None:
         """The body of ``process()`` for a scan that has already been dequeued (``ProcessLoop`` drains the
-        input queue in batches)."""
+        input queue in batches).  ``defer_result=True`` (resident mode) only enqueues the
+        registration; ``flush_results()`` then appends the poses of all deferred scans to
+        ``previous_transformation`` with one device synchronisation for the whole batch."""
+        self._defer = bool(defer_result) and self._mode == "resident"
+        try:
+            self._process_records(scan)
+        finally:
+            self._defer = False
+
+    def flush_results(self) -> int:
+        """Collect the results of the scans submitted with ``defer_result=True``; returns how many."""
+        n = len(self._pending_first)
+        if n == 0:
+            return 0
+        results = self._engine.slam_results(n)
+        for first, res in zip(self._pending_first, results):
+            if first:
+                continue  # the first scan is the map frame: no registration (icp_processor.py:53-56)
+            self.last_result = res
+            self.previous_transformation.append(res.matrix())
+        self._pending_first = []
+        return n
+
+    def _process_records(self, scan) -> None:
         if scan is not None:
             self.logger.debug(f"{len(scan)} points received from queue")
             self.logger.info(f"pcs processed so far: {self.point_clouds_in_map}")
@@ -144,6 +169,7 @@ class B200ICPProcessor(ProcessPointClouds):
         return self.global_map
 
     def reset(self) -> None:
+        self._pending_first = []
         if self._resident_ready:
             self._engine.map_reset()
         self._raw_map = None
@@ -158,12 +184,17 @@ class B200ICPProcessor(ProcessPointClouds):
             eng.map_init(self._map_voxel, self._map_origin, self._max_corr, self._map_capacity)
             self._resident_ready = True
         first = self.point_clouds_in_map == 0
+        defer = self._defer and pts4 is not None
         if pts4 is not None:
-            res = eng.slam_scan_dev(pts4, self._voxel, self._params, want_result=True)
+            res = eng.slam_scan_dev(pts4, self._voxel, self._params, want_result=not defer)
         else:
             res = eng.slam_scan(pts, self._voxel, self._params)
+        if defer:
+            self._pending_first.append(first)
         if first:
             self.point_clouds_in_map += 1  # icp_processor.py:54 (the caller increments once more)
+            return
+        if defer:
             return
         self.last_result = res
         self.previous_transformation.append(res.matrix())

@@ -98,12 +98,17 @@ class ProcessLoop:
         if not scans:
             return 0
         take = getattr(self.processor, "process_records", None)
+        flush = getattr(self.processor, "flush_results", None)
         for scan in scans:
-            if take is not None:
+            if take is not None and flush is not None:
+                take(scan, defer_result=True)  # enqueue only: the batch's poses are read back once, below
+            elif take is not None:
                 take(scan)
             else:  # a reference-style processor that dequeues for itself
                 self.data_transfer.pixel_depth_map_queue.put(scan)
                 self.processor.process()
+        if take is not None and flush is not None:
+            flush()
         self.scans_processed += len(scans)
         self.batches += 1
         if publish_latest(self.data_transfer, self.processor.global_map):
