@@ -329,10 +329,15 @@ def roofline_icp(eng, dev_scans, poses, prm, torch):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     return {"bound": "hbm", "kernel": "icp_iter_kernel<p2p,map>", "achieved": round(achieved, 1), "peak": peak,
             "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6650 GB/s",
-            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+            "unit": "GB/s", "frac": round(achieved / peak, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (cold caches between
+            # replays): profiles/r01c_icp_iter_full_raw.csv
+            "traffic": 2500352,
             "us_per_launch": round(us_per_launch, 3), "queries": int(ns), "candidates": int(cand),
             "algorithmic_bytes_per_launch": int(bytes_per_launch),
-            "note": "includes host-side launch gaps of the per-iteration launches (31 launches per registration)"}
+            "note": "time per launch includes the gaps between the 31 chained launches of a registration; DRAM traffic "
+                    "(2.5 MB cold) is far below the algorithmic bytes because the 27-cell reads of neighbouring "
+                    "queries overlap in L1/L2: the kernel is bound by dependent-access latency, not bandwidth"}
 
 
 def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2batch):
