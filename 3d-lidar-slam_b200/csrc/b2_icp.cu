@@ -636,7 +636,7 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
                 const int* __restrict__ tgt_offs, IcpParams prm, IcpState* __restrict__ states,
                 double* __restrict__ partial, int* __restrict__ tickets, IcpResultDev* __restrict__ results,
                 int* __restrict__ corr_out, int* __restrict__ ndone, double* __restrict__ d2_out,
-                int search_only) {
+                int search_only, unsigned long long loop_handle) {
     constexpr int NT = MODE == 0 ? 17 : 29;  // live accumulator terms
     const int pair = blockIdx.y;
     IcpState* st = states + pair;
@@ -681,7 +681,11 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
         se = ns_dev ? min(*ns_dev, ns_max) : ns_max;
     }
     __syncthreads();
-    if (sState.done) return;
+    if (sState.done) {  // (as the body of a graph WHILE node: make sure the loop ends)
+        if (loop_handle && threadIdx.x == 0 && blockIdx.x == 0)
+            cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, 0u);
+        return;
+    }
     const double* sT = sState.T;
     const double* sPivot = sState.pivot;
 
@@ -723,6 +727,8 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     if (threadIdx.x == 0) {
         tickets[pair] = 0;
         icp_step<MODE>(sSum, se - sb, prm, sState, st, results + pair, ndone);
+        // body of a CUDA-graph WHILE node (single pair): run another step unless the registration is done
+        if (loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, st->done ? 0u : 1u);
     }
     B2_TS(2);
 }
@@ -1259,12 +1265,12 @@ template <int MODE, int IS_MAP>
 void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, const int* ns_dev, int ns_max,
                  const GridView& g, const float4* nrm, const int* tgt_offs, const IcpParams& prm, IcpState* st,
                  double* partial, int* tickets, IcpResultDev* res, int* corr, int* ndone, double* d2_out,
-                 int search_only) {
+                 int search_only, cudaStream_t stream, unsigned long long loop_handle) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = 0;
-    cfg.stream = c->stream;
+    cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1274,7 +1280,7 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
     cudaLaunchKernelEx(&cfg, icp_iter_kernel<MODE, IS_MAP>, src, src_offs, ns_dev, ns_max,
                        (const CellEntry*)g.entries, g.mask, (const float4*)g.pts, (const VoxEntry*)g.vox,
                        (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets, res, corr, ndone, d2_out,
-                       search_only);
+                       search_only, loop_handle);
 }
 
 template <int MODE, int KIND>
@@ -1399,6 +1405,7 @@ int icp_configure(Context* c) {
     return B2_OK;
 }
 
+constexpr int kChainSteps = 40;  // captured scan step: steps launched back to back before the WHILE node takes over
 constexpr long long kSweepMinQueries = 2LL * kCtasPerSm * kSMs * kThreads;  // ~190 k queries in flight
 
 int icp_grid_x(int ns_max, int n_pairs, int kind) {
@@ -1484,10 +1491,20 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         for (auto& e : evs) cudaEventCreate(&e);
         cudaEventRecord(evs[0], c->stream);
     }
-    for (int it = 0; it < launches; ++it) {
+    // Inside a captured scan step with a long iteration budget (the reference default is 500) only the first
+    // kChainSteps steps are chained launches (programmatic dependent launch: the cheapest per step); the rest
+    // of the A.3 loop is a CUDA-graph WHILE node whose body is ONE step kernel.  The solving CTA clears the
+    // loop condition when the registration is done, so a replay runs the steps it needs instead of
+    // max_iteration + 1 launches of which most return at once (500: 985 -> ~495 us per scan).
+    // B2_ICP_WHILE=0 disables the loop node, =1 uses it for every step.
+    static const char* while_env = getenv("B2_ICP_WHILE");
+    const int while_mode = while_env ? atoi(while_env) : -1;
+    const bool can_while = c->capturing && n_pairs == 1 && !sweep && !search_only && !corr_out && !d2_out && while_mode != 0;
+    const int chained = !can_while ? launches : (while_mode == 1 ? 0 : (launches > kChainSteps ? kChainSteps : launches));
+    auto launch_one = [&](cudaStream_t launch_stream, unsigned long long loop_handle) {
 #define B2_ICP_LAUNCH(M, K)                                                                                   \
     launch_iter<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
-                      tickets, results_dev, corr_out, ndone, d2_out, search_only)
+                      tickets, results_dev, corr_out, ndone, d2_out, search_only, launch_stream, loop_handle)
 #define B2_ICP_SWEEP(M, K)                                                                                     \
     launch_sweep<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
                        tickets, results_dev, corr_out, ndone, d2_out, search_only)
@@ -1506,6 +1523,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         }
 #undef B2_ICP_LAUNCH
 #undef B2_ICP_SWEEP
+    };
+    for (int it = 0; it < chained; ++it) {
+        launch_one(c->stream, 0ull);
         B2_LAUNCH_CHECK(c);
         if (timing) cudaEventRecord(evs[it + 1], c->stream);
         if (check_every > 0 && !search_only && !timing && (it + 1) % check_every == 0 && it + 1 < launches) {
@@ -1513,6 +1533,31 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
             B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
             if (*host_done >= n_pairs) break;
         }
+    }
+    if (chained < launches) {  // the remaining steps: a WHILE node after the chained launches
+        cudaStreamCaptureStatus cs;
+        cudaGraph_t parent = nullptr;
+        const cudaGraphNode_t* deps = nullptr;
+        size_t n_deps = 0;
+        B2_CUDA_OK(c, cudaStreamGetCaptureInfo(c->stream, &cs, nullptr, &parent, &deps, &n_deps));
+        cudaGraphConditionalHandle handle;
+        B2_CUDA_OK(c, cudaGraphConditionalHandleCreate(&handle, parent, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams np = {};
+        np.type = cudaGraphNodeTypeConditional;
+        np.conditional.handle = handle;
+        np.conditional.type = cudaGraphCondTypeWhile;
+        np.conditional.size = 1;
+        cudaGraphNode_t loop_node;
+        B2_CUDA_OK(c, cudaGraphAddNode(&loop_node, parent, deps, n_deps, &np));
+        // the body is captured through the copy stream (capture only: nothing runs on that stream)
+        B2_CUDA_OK(c, cudaStreamBeginCaptureToGraph(c->copy_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
+                                                    cudaStreamCaptureModeThreadLocal));
+        launch_one(c->copy_stream, (unsigned long long)handle);
+        cudaGraph_t body = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->copy_stream, &body);
+        B2_LAUNCH_CHECK(c);
+        B2_CUDA_OK(c, e);
+        B2_CUDA_OK(c, cudaStreamUpdateCaptureDependencies(c->stream, &loop_node, 1, cudaStreamSetCaptureDependencies));
     }
     if (timing) {
         cudaStreamSynchronize(c->stream);

@@ -481,3 +481,32 @@ def test_deferred_results_equal_per_scan_results(engine, b2):
     assert [r.iterations for r in engine.slam_results(3)] == [r.iterations for r in sync[-3:]]
     with pytest.raises(b2.B2Error, match="results asked"):
         engine.slam_results(100000)
+
+
+@pytest.mark.parametrize("budget,rel", [(500, 1e-6), (57, 0.0)])
+def test_slam_sequence_long_iteration_budget_uses_loop_node(engine, b2, budget, rel):
+    """Iteration budgets above the chained-launch window run the tail of the A.3 loop as a CUDA-graph WHILE
+    node once the step is captured (third scan on): the reference default of 500 iterations must stop at
+    convergence exactly like the oracle, and with the convergence test disabled (rel = 0) the loop must run
+    every one of the 57 steps (40 chained + 17 loop-node trips)."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(13, length=12.0)
+    poses = synth.corridor_trajectory(scene, 6, seed=13)
+    origin = np.array([-20.0, -20.0, -20.0])
+    engine.map_init(0.05, origin, 0.05, 1 << 18)
+    engine.set_pose(np.eye(4))
+    ref = pipeline.ResidentSequence(0.05, origin, ds_voxel=0.02, max_corr=0.05, max_iteration=budget,
+                                    relative_fitness=rel, relative_rmse=rel)
+    prm = b2.make_params(0.05, budget, rel_fitness=rel, rel_rmse=rel)
+    for k, pose in enumerate(poses):
+        scan = synth.render_scan(scene, pose, seed=300 + k).numpy()
+        res = engine.slam_scan(scan, 0.02, prm)
+        ores = ref.process(scan)
+        if k == 0:
+            continue
+        assert res.iterations == ores.iterations, k
+        if rel == 0.0:
+            assert res.iterations == budget
+        assert_transform_close(res.matrix(), ores.transformation)
+        assert res.fitness == pytest.approx(ores.fitness, abs=2e-4)
