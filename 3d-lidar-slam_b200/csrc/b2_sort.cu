@@ -52,42 +52,62 @@ sort_hist_kernel(const unsigned long long* __restrict__ keysA, const unsigned lo
     hist[threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
 }
 
-// Exclusive scan of `total` counters in place, one CTA of 1024 threads.
+// Exclusive scan of `total` counters in place, one CTA of 1024 threads (`total` is a multiple of 256 and the
+// buffer is 16-byte aligned).  The counters are walked in chunks of 8192: every thread loads two uint4 that are
+// adjacent to its neighbours' (coalesced), scans its eight values in registers, and the CTA scans the
+// per-thread sums; a running carry links the chunks.
 __global__ void __launch_bounds__(1024)
 sort_scan_kernel(unsigned* __restrict__ hist, int total, const SortCtl* __restrict__ ctl, int pass) {
     pdl_enter();
     if (pass >= ctl->npasses) return;
     __shared__ unsigned warp_sums[32];
-    const int per = (total + 1023) / 1024;
-    const int b = threadIdx.x * per;
-    const int e = min(total, b + per);
-    unsigned s = 0;
-    for (int i = b; i < e; ++i) s += hist[i];
+    __shared__ unsigned carry_s;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned incl = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_sums[w] = incl;
+    if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    if (w == 0) {
-        unsigned v = warp_sums[lane];
-        unsigned inc2 = v;
+    uint4* h4 = reinterpret_cast<uint4*>(hist);
+    const int total4 = total >> 2;
+    for (int base = 0; base < total4; base += 2048) {
+        // thread t owns uint4 #(base + 2t) and #(base + 2t + 1): eight consecutive counters
+        const int i0 = base + 2 * (int)threadIdx.x;
+        uint4 a = make_uint4(0, 0, 0, 0), b = a;
+        if (i0 < total4) a = h4[i0];
+        if (i0 + 1 < total4) b = h4[i0 + 1];
+        const unsigned s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+        unsigned incl = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned t = __shfl_up_sync(0xffffffffu, inc2, o);
-            if (lane >= o) inc2 += t;
+            unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        warp_sums[lane] = inc2 - v;
-    }
-    __syncthreads();
-    unsigned run = warp_sums[w] + incl - s;
-    for (int i = b; i < e; ++i) {
-        unsigned v = hist[i];
-        hist[i] = run;
-        run += v;
+        const unsigned carry = carry_s;  // (written two barriers ago; rewritten only after the next one)
+        if (lane == 31) warp_sums[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            unsigned v = warp_sums[lane];
+            unsigned inc2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned t = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += t;
+            }
+            warp_sums[lane] = inc2 - v;
+            if (lane == 31) carry_s = carry + inc2;  // read by everybody after the next barrier
+        }
+        __syncthreads();
+        unsigned run = carry + warp_sums[w] + incl - s;
+        uint4 oa, ob;
+        oa.x = run; run += a.x;
+        oa.y = run; run += a.y;
+        oa.z = run; run += a.z;
+        oa.w = run; run += a.w;
+        ob.x = run; run += b.x;
+        ob.y = run; run += b.y;
+        ob.z = run; run += b.z;
+        ob.w = run;
+        if (i0 < total4) h4[i0] = oa;
+        if (i0 + 1 < total4) h4[i0 + 1] = ob;
+        __syncthreads();  // warp_sums / carry_s are rewritten by the next chunk
     }
 }
 
