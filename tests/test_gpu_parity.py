@@ -510,3 +510,43 @@ def test_slam_sequence_long_iteration_budget_uses_loop_node(engine, b2, budget, 
             assert res.iterations == budget
         assert_transform_close(res.matrix(), ores.transformation)
         assert res.fitness == pytest.approx(ores.fitness, abs=2e-4)
+
+
+def _one_step(engine, b2, src, tgt, gate, driver_name="group"):
+    engine.set_icp_driver(driver_name)
+    try:
+        res, corr = engine.icp(engine.pack(src.astype(np.float32)), engine.pack(tgt.astype(np.float32)),
+                               b2.make_params(gate, 1), want_corr=True)
+    finally:
+        engine.set_icp_driver("auto")
+    ores = orc.registration_icp(f64(src.astype(np.float32)), f64(tgt.astype(np.float32)), gate, max_iteration=1)
+    np.testing.assert_array_equal(corr.cpu().numpy(), ores.correspondence)
+    return res, ores
+
+
+@pytest.mark.parametrize("case", ["coplanar", "reflection", "three_points", "coplanar_sweep"])
+def test_se3_solve_special_covariances(engine, b2, case):
+    """The on-device Umeyama step away from the fast path (Newton polar iteration needs det(C) > 0): rank-2
+    covariances (coplanar clouds, three points) and a covariance whose best orthogonal fit is a reflection
+    must come out as the proper rotation Eigen's umeyama / the oracle returns."""
+    rng = np.random.default_rng(42)
+    if case.startswith("coplanar"):
+        tgt = np.concatenate([rng.uniform(0.0, 4.0, (400, 2)), np.full((400, 1), 1.25)], axis=1)
+    elif case == "three_points":
+        tgt = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.2], [0.1, 1.3, -0.1]])
+    else:
+        tgt = rng.uniform(-2.0, 2.0, (300, 3))
+    a = 0.02
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    src = (tgt - [0.01, -0.02, 0.0]) @ R  # small in-plane motion: nearest neighbours are the true pairs
+    gate = 0.5
+    if case == "reflection":
+        # squash and mirror the source through the z = 0 plane with noise: the unconstrained optimum has det < 0
+        tgt = tgt * [1.0, 1.0, 0.02]
+        src = tgt * [1.0, 1.0, -1.0] + rng.normal(scale=1e-3, size=tgt.shape)
+    res, ores = _one_step(engine, b2, src, tgt, gate, "sweep" if case.endswith("sweep") else "group")
+    assert res.fitness == ores.fitness == 1.0
+    T = res.matrix()
+    assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-9
+    np.testing.assert_allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-9)
+    assert_transform_close(T, ores.transformation)
