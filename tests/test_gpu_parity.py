@@ -550,3 +550,25 @@ def test_se3_solve_special_covariances(engine, b2, case):
     assert abs(np.linalg.det(T[:3, :3]) - 1.0) < 1e-9
     np.testing.assert_allclose(T[:3, :3] @ T[:3, :3].T, np.eye(3), atol=1e-9)
     assert_transform_close(T, ores.transformation)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_lattice_clouds_exact_boundaries_and_ties(engine, seed, driver):
+    """Points on a 1/8 m lattice (every coordinate exactly representable): voxel faces are hit exactly, many
+    points coincide, and nearest-neighbour distances tie exactly — keys, occupancy, correspondences and d2 must
+    still be bit-identical to the oracle (ties -> lowest target index; d2 < r2 strict)."""
+    rng = np.random.default_rng(seed)
+    tgt = (rng.integers(-40, 40, (6000, 3)) * 0.125).astype(np.float32)
+    src = (rng.integers(-40, 40, (3000, 3)) * 0.125).astype(np.float32)
+    for voxel in (0.25, 0.125, 0.3):
+        cent, keys = engine.voxel_downsample(engine.pack(tgt), voxel)
+        oc, ok, on = orc.voxel_downsample(f64(tgt), voxel)
+        np.testing.assert_array_equal(keys.cpu().numpy(), ok)
+        np.testing.assert_array_equal(counts(cent), on)
+        np.testing.assert_allclose(xyz(cent), oc, rtol=CENT_RTOL, atol=CENT_ATOL)
+    for radius in (0.125, 0.25, 0.3):  # 0.125 / 0.25: neighbours at exactly the radius must be rejected
+        idx, d2 = engine.nn_search(engine.pack(src), engine.pack(tgt), radius)
+        oidx, od2 = orc.nn_search(f64(src), f64(tgt), radius)
+        np.testing.assert_array_equal(idx.cpu().numpy(), oidx)
+        np.testing.assert_array_equal(d2.cpu().numpy(), od2)
+        assert (oidx >= 0).any() and (oidx < 0).any()
