@@ -25,7 +25,8 @@ EXPORTS = [
     "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
-    "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results",
+    "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results", "b2_icp_batch_p2l",
+    "b2_estimate_normals_batch",
 ]
 
 
@@ -98,6 +99,8 @@ def load():
         "b2_slam_set_pose": [vp, pd],
         "b2_slam_get_pose": [vp, pd],
         "b2_icp_batch": [vp, vp, vp, i32, vp, vp, i32, i32, f64, vp, C.POINTER(IcpParams), vp],
+        "b2_icp_batch_p2l": [vp, vp, vp, i32, vp, vp, i32, i32, f64, f64, i32, vp, C.POINTER(IcpParams), vp],
+        "b2_estimate_normals_batch": [vp, vp, vp, i32, i32, f64, i32, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
@@ -423,19 +426,37 @@ class Engine:
         return out.reshape(4, 4)
 
     # -- batch ----------------------------------------------------------------
-    def icp_batch(self, src, src_offsets, tgt, tgt_offsets, params: IcpParams, ds_voxel: float = 0.0, init=None):
+    def icp_batch(self, src, src_offsets, tgt, tgt_offsets, params: IcpParams, ds_voxel: float = 0.0, init=None,
+                  normal_radius: float = 0.0, normal_max_nn: int = 20):
         """src/tgt: CUDA float32 [sum,4]; offsets: CUDA int32 [n_pairs+1].
-        -> CUDA uint8 tensor viewable as RESULT_DTYPE records (stays on the device for NCCL gathers)."""
+        -> CUDA uint8 tensor viewable as RESULT_DTYPE records (stays on the device for NCCL gathers).
+        ``params.mode == P2L``: the normals of every (down-sampled) target are estimated first with
+        (``normal_radius``, ``normal_max_nn``)."""
         torch = self.torch
         src, tgt = self._pts(src), self._pts(tgt)
         n_pairs = src_offsets.numel() - 1
         assert src_offsets.dtype == torch.int32 and tgt_offsets.dtype == torch.int32
         res = self.empty((n_pairs, C.sizeof(IcpResult)), torch.uint8)
-        self._check(self.lib.b2_icp_batch(self.h, src.data_ptr(), src_offsets.data_ptr(), src.shape[0],
-                                          tgt.data_ptr(), tgt_offsets.data_ptr(), tgt.shape[0], n_pairs,
-                                          float(ds_voxel), init.data_ptr() if init is not None else None,
-                                          C.byref(params), res.data_ptr()))
+        ip = init.data_ptr() if init is not None else None
+        if params.mode == P2L:
+            self._check(self.lib.b2_icp_batch_p2l(self.h, src.data_ptr(), src_offsets.data_ptr(), src.shape[0],
+                                                  tgt.data_ptr(), tgt_offsets.data_ptr(), tgt.shape[0], n_pairs,
+                                                  float(ds_voxel), float(normal_radius), int(normal_max_nn), ip,
+                                                  C.byref(params), res.data_ptr()))
+        else:
+            self._check(self.lib.b2_icp_batch(self.h, src.data_ptr(), src_offsets.data_ptr(), src.shape[0],
+                                              tgt.data_ptr(), tgt_offsets.data_ptr(), tgt.shape[0], n_pairs,
+                                              float(ds_voxel), ip, C.byref(params), res.data_ptr()))
         return res
+
+    def estimate_normals_batch(self, pts, offsets, radius: float, max_nn: int):
+        """Normals of a batch of clouds (concatenated rows, CUDA int32 [n_clouds+1] offsets)."""
+        pts = self._pts(pts)
+        assert offsets.dtype == self.torch.int32
+        out = self.empty_points(pts.shape[0])
+        self._check(self.lib.b2_estimate_normals_batch(self.h, pts.data_ptr(), offsets.data_ptr(), pts.shape[0],
+                                                       offsets.numel() - 1, float(radius), int(max_nn), out.data_ptr()))
+        return out
 
 
 def _dptr3(v):

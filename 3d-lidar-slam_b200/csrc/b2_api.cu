@@ -466,7 +466,7 @@ int b2_estimate_normals(b2_handle h, const float* pts_dev, int n, double radius,
     if (n < 0 || (n > 0 && (!pts_dev || !out_normals_dev))) return set_error(c, B2_ERR_INVALID, "b2_estimate_normals: bad arguments");
     if (n == 0) return B2_OK;
     auto body = [&]() -> int {
-        B2_TRY(estimate_normals(c, (const float4*)pts_dev, n, nullptr, radius, max_nn, (float4*)out_normals_dev));
+        B2_TRY(estimate_normals(c, (const float4*)pts_dev, n, nullptr, nullptr, 1, radius, max_nn, (float4*)out_normals_dev));
         return check_status(c);
     };
     B2_RETRY_WIDE(c, body());
@@ -917,16 +917,19 @@ int b2_map_stencil_candidates(b2_handle h, const float* src_dev, int ns, const d
     return B2_OK;
 }
 
-int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total, const float* tgt_dev,
-                 const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel, const double* init_dev,
-                 const b2_icp_params* params, b2_icp_result* results_dev) {
-    CTX(h);
+static int icp_batch_impl(Context* c, const float* src_dev, const int* src_offsets_dev, int src_total,
+                          const float* tgt_dev, const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel,
+                          double normal_radius, int normal_max_nn, const double* init_dev, const b2_icp_params* params,
+                          b2_icp_result* results_dev) {
     B2_TRY(check_params(c, params));
     if (n_pairs <= 0 || src_total <= 0 || tgt_total <= 0 || !src_dev || !tgt_dev || !src_offsets_dev ||
         !tgt_offsets_dev || !results_dev)
         return set_error(c, B2_ERR_INVALID, "b2_icp_batch: empty batch or NULL argument");
     if (n_pairs > 32768) return set_error(c, B2_ERR_INVALID, "b2_icp_batch: at most 32768 pairs per call (got %d)", n_pairs);
-    if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "b2_icp_batch: point-to-point only");
+    const bool p2l = params->mode == B2_ICP_POINT_TO_PLANE;
+    if (p2l && (!(normal_radius > 0.0) || normal_max_nn < 1))
+        return set_error(c, B2_ERR_INVALID, "point-to-plane batch: normal_radius > 0 and normal_max_nn >= 1 required "
+                                            "(use b2_icp_batch_p2l)");
     HintGuard guard(c, 8);
     const float4* src = (const float4*)src_dev;
     const float4* tgt = (const float4*)tgt_dev;
@@ -943,11 +946,52 @@ int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, 
         B2_TRY(voxel_downsample(c, tgt, tgt_total, nullptr, tgt_offsets_dev, n_pairs, ds_voxel, 0, nullptr, nullptr, o2, nullptr));
         src = sd; tgt = td; soffs = so; toffs = to;
     }
+    const float4* normals = nullptr;
+    if (p2l) {  // icp_processor.py:94-99 on every (down-sampled) target of the batch
+        B2_WS(c, nrm, float4, WS_BATCH_C, sizeof(float4) * (size_t)tgt_total);
+        B2_TRY(estimate_normals(c, tgt, tgt_total, nullptr, toffs, n_pairs, normal_radius, normal_max_nn, nrm));
+        normals = nrm;
+    }
     GridView g;
     B2_TRY(grid_build(c, tgt, tgt_total, nullptr, toffs, n_pairs, params->max_correspondence_distance, WS_GRID_ENTRIES, &g));
-    B2_TRY(icp_run(c, src, src_total, soffs, nullptr, n_pairs, g, nullptr, toffs, init_dev, to_internal(params),
+    B2_TRY(icp_run(c, src, src_total, soffs, nullptr, n_pairs, g, normals, toffs, init_dev, to_internal(params),
                    (IcpResultDev*)results_dev, nullptr, nullptr, 0, 0));
     return B2_OK;
+}
+
+int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total, const float* tgt_dev,
+                 const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel, const double* init_dev,
+                 const b2_icp_params* params, b2_icp_result* results_dev) {
+    CTX(h);
+    if (params && params->mode != B2_ICP_POINT_TO_POINT)
+        return set_error(c, B2_ERR_INVALID, "b2_icp_batch: point-to-point only (b2_icp_batch_p2l estimates the normals)");
+    return icp_batch_impl(c, src_dev, src_offsets_dev, src_total, tgt_dev, tgt_offsets_dev, tgt_total, n_pairs, ds_voxel,
+                          0.0, 0, init_dev, params, results_dev);
+}
+
+int b2_icp_batch_p2l(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total, const float* tgt_dev,
+                     const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel, double normal_radius,
+                     int normal_max_nn, const double* init_dev, const b2_icp_params* params, b2_icp_result* results_dev) {
+    CTX(h);
+    if (params && params->mode != B2_ICP_POINT_TO_PLANE)
+        return set_error(c, B2_ERR_INVALID, "b2_icp_batch_p2l: params->mode must be B2_ICP_POINT_TO_PLANE");
+    return icp_batch_impl(c, src_dev, src_offsets_dev, src_total, tgt_dev, tgt_offsets_dev, tgt_total, n_pairs, ds_voxel,
+                          normal_radius, normal_max_nn, init_dev, params, results_dev);
+}
+
+int b2_estimate_normals_batch(b2_handle h, const float* pts_dev, const int* offsets_dev, int total, int n_clouds,
+                              double radius, int max_nn, float* out_normals_dev) {
+    CTX(h);
+    if (total < 0 || n_clouds <= 0 || n_clouds > 32768 || (total > 0 && (!pts_dev || !offsets_dev || !out_normals_dev)))
+        return set_error(c, B2_ERR_INVALID, "b2_estimate_normals_batch: bad arguments");
+    if (total == 0) return B2_OK;
+    HintGuard guard(c, 8);
+    auto body = [&]() -> int {
+        B2_TRY(estimate_normals(c, (const float4*)pts_dev, total, nullptr, offsets_dev, n_clouds, radius, max_nn,
+                                (float4*)out_normals_dev));
+        return check_status(c);
+    };
+    B2_RETRY_WIDE(c, body());
 }
 
 }  // extern "C"

@@ -414,8 +414,8 @@ int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev
                       unsigned long long* total_dev);
 
 // b2_normals.cu
-int estimate_normals(Context* c, const float4* pts, int n_max, const int* n_dev, double radius, int max_nn,
-                     float4* normals_out);
+int estimate_normals(Context* c, const float4* pts, int n_max, const int* n_dev, const int* cloud_offsets, int n_clouds,
+                     double radius, int max_nn, float4* normals_out);
 
 // b2_filters.cu
 int radius_outlier_mask(Context* c, const float4* pts, int n, int nb_points, double radius, unsigned char* keep);

@@ -133,13 +133,15 @@ __device__ __forceinline__ int group_sum(int v, unsigned gmask) {
 
 __global__ void __launch_bounds__(kThreads)
 normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max,
-               const CellEntry* __restrict__ entries, unsigned mask, const float4* __restrict__ gpts,
-               const GridMeta* __restrict__ meta, double radius, int max_nn, float4* __restrict__ normals) {
+               const int* __restrict__ offs, int n_clouds, const CellEntry* __restrict__ entries, unsigned mask,
+               const float4* __restrict__ gpts, const GridMeta* __restrict__ metas, double radius, int max_nn,
+               float4* __restrict__ normals) {
     // staging area of a group for the capped case: (d2 bit pattern, index, position) of its in-radius
     // candidates, ranked against each other on chip
     __shared__ unsigned long long s_d2[kThreads / kGroup][kStage];
     __shared__ int2 s_ip[kThreads / kGroup][kStage];
-    const int n = n_dev ? min(*n_dev, n_max) : n_max;
+    // (a batch of clouds: offs[0..n_clouds] delimit them, every cloud has its own grid origin and key prefix)
+    const int n = offs ? offs[n_clouds] : (n_dev ? min(*n_dev, n_max) : n_max);
     const int lane = threadIdx.x & 31;
     const int g = lane & (kGroup - 1), gi = lane / kGroup;  // lane in group, group in warp
     const int gslot = threadIdx.x / kGroup;
@@ -147,7 +149,6 @@ normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, in
     const int warp_global = blockIdx.x * kWarps + (threadIdx.x >> 5);
     const int warp_stride = gridDim.x * kWarps;
     const double r2 = dmul(radius, radius);
-    const double ox = meta->origin[0], oy = meta->origin[1], oz = meta->origin[2], cell = meta->cell;
     const unsigned long long r2bits = (unsigned long long)__double_as_longlong(r2);
 
     // a warp owns 32 consecutive points: 8 rounds of 4 concurrent group searches, then every lane
@@ -161,15 +162,25 @@ normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, in
             const int q = base + r * (32 / kGroup) + gi;
             const bool valid = q < n;
             double Px = 0.0, Py = 0.0, Pz = 0.0;
-            int cx = 0, cy = 0, cz = 0;
+            int cx = 0, cy = 0, cz = 0, cloud = 0;
             if (g == 0 && valid) {
                 const float4 p = __ldg(pts + q);
                 Px = p.x; Py = p.y; Pz = p.z;
-                cx = voxel_coord(Px, ox, cell);
-                cy = voxel_coord(Py, oy, cell);
-                cz = voxel_coord(Pz, oz, cell);
+                if (offs) {  // offs[cloud] <= q < offs[cloud + 1]
+                    int lo = 0, hi = n_clouds;
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (__ldg(offs + mid) <= q) lo = mid; else hi = mid;
+                    }
+                    cloud = lo;
+                }
+                const GridMeta* meta = metas + cloud;
+                cx = voxel_coord(Px, meta->origin[0], meta->cell);
+                cy = voxel_coord(Py, meta->origin[1], meta->cell);
+                cz = voxel_coord(Pz, meta->origin[2], meta->cell);
             }
             const int lead = gi * kGroup;
+            cloud = __shfl_sync(kFull, cloud, lead);
             Px = __shfl_sync(kFull, Px, lead);
             Py = __shfl_sync(kFull, Py, lead);
             Pz = __shfl_sync(kFull, Pz, lead);
@@ -187,7 +198,7 @@ normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, in
                 const int c3 = (c * 171) >> 9, c9 = (c * 57) >> 9;
                 const int nx = cx + c9 - 1, ny = cy + (c3 - 3 * c9) - 1, nz = cz + (c - 3 * c3) - 1;
                 hit[k] = valid && c < 27 && nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536;
-                key[k] = pair_cell_key(0u, nx, ny, nz);
+                key[k] = pair_cell_key((unsigned)cloud, nx, ny, nz);
                 hpos[k] = cell_hash(key[k]) & mask;
             }
 #pragma unroll
@@ -335,16 +346,16 @@ normals_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, in
 
 }  // namespace
 
-int estimate_normals(Context* c, const float4* pts, int n_max, const int* n_dev, double radius, int max_nn,
-                     float4* normals_out) {
+int estimate_normals(Context* c, const float4* pts, int n_max, const int* n_dev, const int* offs, int n_clouds,
+                     double radius, int max_nn, float4* normals_out) {
     if (n_max <= 0) return B2_OK;
     if (!(radius > 0.0) || max_nn < 1) return set_error(c, B2_ERR_INVALID, "estimate_normals: radius > 0 and max_nn >= 1 required");
     GridView g;
-    B2_TRY(grid_build(c, pts, n_max, n_dev, nullptr, 1, radius, WS_GRID2_ENTRIES, &g));
+    B2_TRY(grid_build(c, pts, n_max, n_dev, offs, offs ? n_clouds : 1, radius, WS_GRID2_ENTRIES, &g));
     int blocks = div_up(div_up(n_max, 32), kWarps);
     if (blocks > kSMs * 8) blocks = kSMs * 8;
-    normals_kernel<<<blocks, kThreads, 0, c->stream>>>(pts, n_dev, n_max, g.entries, g.mask, g.pts, g.meta, radius,
-                                                       max_nn, normals_out);
+    normals_kernel<<<blocks, kThreads, 0, c->stream>>>(pts, n_dev, n_max, offs, offs ? n_clouds : 1, g.entries, g.mask,
+                                                       g.pts, g.meta, radius, max_nn, normals_out);
     B2_LAUNCH_CHECK(c);
     return B2_OK;
 }

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--pairs", type=int, default=148)
 ap.add_argument("--iters", type=int, default=6)
 ap.add_argument("--points", type=int, default=49152)
+ap.add_argument("--p2l", action="store_true", help="point-to-plane batch (normals of every target estimated first)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 eng = b2.Engine(0)
@@ -26,12 +27,12 @@ src = torch.cat((srcs * reps)[: args.pairs]).to(dev)
 tgt = torch.cat((tgts * reps)[: args.pairs]).to(dev)
 so = torch.arange(0, args.pairs + 1, dtype=torch.int32, device=dev) * args.points
 S4, T4 = eng.pack(src), eng.pack(tgt)
-prm = b2.make_params(0.05, args.iters)
+prm = b2.make_params(0.05, args.iters, mode=b2.P2L if args.p2l else b2.P2P)
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for _ in range(2):
     with torch.cuda.stream(eng.stream):
         ev0.record()
-        res = eng.icp_batch(S4, so, T4, so, prm, ds_voxel=0.02)
+        res = eng.icp_batch(S4, so, T4, so, prm, ds_voxel=0.02, normal_radius=0.04, normal_max_nn=20)
         ev1.record()
     eng.synchronize()
 print("ms", ev0.elapsed_time(ev1), "fitness", float(batch.records_view(res)["fitness"].mean()))

@@ -198,6 +198,16 @@ int b2_slam_get_pose(b2_handle h, double* T);
 int b2_icp_batch(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total,
                  const float* tgt_dev, const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel,
                  const double* init_dev, const b2_icp_params* params, b2_icp_result* results_dev);
+/* Point-to-plane batch (BASELINE config 3 over many pairs): the normals of every (down-sampled) target are
+ * estimated first — estimate_normals(KDTreeSearchParamHybrid(normal_radius, normal_max_nn)), icp_processor.py:94-99
+ * uses radius = 2 voxels, max_nn = 20 — then the batch runs with params->mode = B2_ICP_POINT_TO_PLANE. */
+int b2_icp_batch_p2l(b2_handle h, const float* src_dev, const int* src_offsets_dev, int src_total, const float* tgt_dev,
+                     const int* tgt_offsets_dev, int tgt_total, int n_pairs, double ds_voxel, double normal_radius,
+                     int normal_max_nn, const double* init_dev, const b2_icp_params* params, b2_icp_result* results_dev);
+/* b2_estimate_normals over a batch of clouds (concatenated rows, int32 [n_clouds+1] device offsets): neighbours are
+ * searched inside a point's own cloud only. */
+int b2_estimate_normals_batch(b2_handle h, const float* pts_dev, const int* offsets_dev, int total, int n_clouds,
+                              double radius, int max_nn, float* out_normals_dev);
 
 #ifdef __cplusplus
 }

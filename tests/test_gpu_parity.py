@@ -572,3 +572,41 @@ def test_lattice_clouds_exact_boundaries_and_ties(engine, seed, driver):
         np.testing.assert_array_equal(idx.cpu().numpy(), oidx)
         np.testing.assert_array_equal(d2.cpu().numpy(), od2)
         assert (oidx >= 0).any() and (oidx < 0).any()
+
+
+def test_batch_normals_and_point_to_plane_match_per_pair_oracle(engine, b2, driver):
+    """b2_estimate_normals_batch / b2_icp_batch_p2l (config 3 over a batch): normals searched inside each cloud
+    only; every pair's registration equals the single-pair oracle run with that pair's normals."""
+    from lidar_slam_b200 import synth
+
+    pairs = [synth.make_pair(s) for s in (3, 4, 5)]
+    srcs = [p[0].numpy()[::2].copy() for p in pairs]
+    tgts = [p[1].numpy()[::2].copy() for p in pairs]
+    tgts[1] = tgts[1][:9000].copy()  # ragged
+    so = np.cumsum([0] + [len(s) for s in srcs]).astype(np.int32)
+    to = np.cumsum([0] + [len(t) for t in tgts]).astype(np.int32)
+    T4 = engine.pack(np.concatenate(tgts))
+    # batched normals on the raw targets == per-cloud normals
+    nb = engine.estimate_normals_batch(T4, torch.from_numpy(to).cuda(), 0.04, 20)
+    for i, t in enumerate(tgts):
+        ni = engine.estimate_normals(engine.pack(t), 0.04, 20)
+        np.testing.assert_array_equal(xyz(nb)[to[i]:to[i + 1]], xyz(ni))
+    # batched point-to-plane with internal down-sampling and normals
+    prm = b2.make_params(0.05, 30, mode=b2.P2L)
+    res = engine.icp_batch(engine.pack(np.concatenate(srcs)), torch.from_numpy(so).cuda(), T4, torch.from_numpy(to).cuda(),
+                           prm, ds_voxel=0.02, normal_radius=0.04, normal_max_nn=20)
+    engine.synchronize()
+    rec = b2.results_to_numpy(res)
+    for i in range(len(pairs)):
+        sd, _, _ = orc.voxel_downsample(f64(srcs[i]), 0.02)
+        td, _, _ = orc.voxel_downsample(f64(tgts[i]), 0.02)
+        td32 = td.astype(np.float32)
+        nrm = engine.estimate_normals(engine.pack(td32), 0.04, 20)  # (GPU normals == oracle up to sign: tested above)
+        ores = orc.registration_icp(f64(sd.astype(np.float32)), f64(td32), 0.05, mode="p2l", tgt_normals=f64(xyz(nrm)),
+                                    max_iteration=30)
+        assert rec["iterations"][i] == ores.iterations, i
+        assert rec["fitness"][i] == ores.fitness, i
+        assert_transform_close(rec["transformation"][i], ores.transformation)
+    with pytest.raises(b2.B2Error, match="normal_radius"):
+        engine.icp_batch(engine.pack(np.concatenate(srcs)), torch.from_numpy(so).cuda(), T4,
+                         torch.from_numpy(to).cuda(), prm, ds_voxel=0.02)
