@@ -1132,18 +1132,20 @@ icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_de
                    double* __restrict__ partial, PersistSync* __restrict__ sync, IcpResultDev* __restrict__ results,
                    int* __restrict__ corr_out, int* __restrict__ ndone) {
     constexpr int NT = MODE == 0 ? 17 : 29;
-    __shared__ double sT[12];
-    __shared__ double sPivot[3];
+    __shared__ IcpState sState;  // every CTA keeps a snapshot of the pair's state: the solver never re-reads it
     __shared__ GridMeta sMeta;
     __shared__ double sAccL[NT][kLeaders];
     __shared__ double sRed[kThreads / 32][kTerms];
     __shared__ double sSum[kTerms];
-    __shared__ int sFlag;  // 1: this CTA was the last arriver; after the barrier: done flag
+    __shared__ int sFlag;  // 1: this CTA was the last arriver of the step
+    const double* sT = sState.T;
+    const double* sPivot = sState.pivot;
 
     const int se = ns_dev ? min(*ns_dev, ns_max) : ns_max;
-    if (threadIdx.x < 12) sT[threadIdx.x] = st->T[threadIdx.x];
-    if (threadIdx.x < 3) sPivot[threadIdx.x] = st->pivot[threadIdx.x];
-    if (threadIdx.x == 0) sMeta = metas[0];
+    if (threadIdx.x < sizeof(IcpState) / 8)
+        reinterpret_cast<double*>(&sState)[threadIdx.x] = reinterpret_cast<const double*>(st)[threadIdx.x];
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(GridMeta) / 8)
+        reinterpret_cast<double*>(&sMeta)[threadIdx.x - 32] = reinterpret_cast<const double*>(metas)[threadIdx.x - 32];
 
     SearchArgs a;
     a.entries = entries; a.vox = vox; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
@@ -1202,35 +1204,25 @@ icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_de
         }
         __syncthreads();
         B2_PTS(3);
-        if (sFlag) {  // last arriver of this step: every partial is visible
-            __threadfence();
+        if (sFlag) {  // last arriver of this step: the ticket ordered every CTA's partial before this point
             grid_fold<NT>(partial, (int)n_cta, sRed, sSum);
             B2_PTS(4);
             if (threadIdx.x == 0) {
-                {
-                    IcpState cur;
-                    for (int k = 0; k < 16; ++k) cur.T[k] = st->T[k];
-                    cur.fitness = st->fitness; cur.rmse = st->rmse;
-                    cur.prev_fitness = st->prev_fitness; cur.prev_rmse = st->prev_rmse;
-                    for (int k = 0; k < 3; ++k) cur.pivot[k] = st->pivot[k];
-                    cur.iter = st->iter; cur.done = st->done; cur.n_corr = st->n_corr; cur.has_prev = st->has_prev;
-                    icp_step<MODE>(sSum, se, prm, cur, st, results, ndone);
-                }
+                icp_step<MODE>(sSum, se, prm, sState, st, results, ndone);
                 B2_PTS(5);
                 __threadfence();
                 st_release_u32(&sync->epoch, step + 1);
             }
         } else if (threadIdx.x == 0) {
-            while (ld_acquire_u32(&sync->epoch) < step + 1) __nanosleep(40);
+            while (ld_acquire_u32(&sync->epoch) < step + 1) __nanosleep(20);
         }
         __syncthreads();
         B2_PTS(6);
-        // pick up the published state (written by another CTA: bypass L1)
-        if (threadIdx.x < 12) sT[threadIdx.x] = __ldcg(&st->T[threadIdx.x]);
-        if (threadIdx.x < 3) sPivot[threadIdx.x] = __ldcg(&st->pivot[threadIdx.x]);
-        if (threadIdx.x == 32) sFlag = __ldcg(&st->done);
+        // pick up the published state (written by another CTA: read it from L2)
+        if (threadIdx.x < sizeof(IcpState) / 8)
+            reinterpret_cast<double*>(&sState)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(st) + threadIdx.x);
         __syncthreads();
-        if (sFlag) break;
+        if (sState.done) break;
     }
 }
 

@@ -9,7 +9,7 @@ scene = bench.build_scene(0)
 print("map voxels", bench.preload_map(eng, scene, torch.device("cuda", 0)))
 scans, poses = bench.make_scans(scene, 3, torch.device("cuda", 0), seed=1)
 sd, _ = eng.voxel_downsample(eng.pack(scans[1]), 0.02, want_keys=False)
-for iters in (12,):
+for iters in (12, 60):
     prm = b2.make_params(0.05, iters, rel_fitness=0.0, rel_rmse=0.0)
     for _ in range(3):
         r = eng.map_icp(sd, prm, init=poses[1])
