@@ -103,3 +103,26 @@ def test_bag_round_trip_and_order(tmp_path):
     with pytest.raises(KeyError):
         w2 = bag.BagWriter(str(tmp_path / "other"))
         w2.write("/nope", b"", 0)
+
+
+def test_cdr_and_rosbridge_round_trip_fuzz():
+    """Property: any well-formed PointCloud2 survives CDR and rosbridge-JSON encoding (random field tables,
+    names of every length mod 4 to exercise the alignment padding, payloads of any size)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    field = st.builds(pc2.PointField, st.text(alphabet="abcxyz_0123456789", min_size=0, max_size=9),
+                      st.integers(0, 2 ** 31 - 1), st.integers(1, 8), st.integers(1, 16))
+    cloud = st.builds(pc2.PointCloud2,
+                      st.builds(pc2.Header, st.builds(pc2.Time, st.integers(-2 ** 31, 2 ** 31 - 1), st.integers(0, 2 ** 32 - 1)),
+                                st.text(alphabet="abcdefghijklmnop/_", max_size=11)),
+                      st.integers(0, 4), st.integers(0, 50), st.lists(field, max_size=5), st.booleans(),
+                      st.integers(0, 64), st.integers(0, 4096), st.binary(max_size=300), st.booleans())
+
+    @settings(max_examples=150, deadline=None)
+    @given(cloud)
+    def check(c):
+        assert pc2.deserialize_cdr(pc2.serialize_cdr(c)) == c
+        assert pc2.from_rosbridge(pc2.to_rosbridge(c)) == c
+
+    check()
