@@ -10,7 +10,9 @@
 //                   distances of every point in the (2m+1)^3 stencil into shared memory, picks the
 //                   k-th smallest with an 8-bit MSB radix select on the fp64 bit patterns, and accepts
 //                   it once it cannot be beaten from outside the stencil (d_k <= (m*cell)^2);
-//                   otherwise the stencil grows by one ring.  mean_i = sum of the k smallest
+//                   otherwise the stencil grows by one ring.  A stencil with more candidates than the
+//                   buffer holds is swept twice more: histogram of d^2 -> bin of the k-th -> buffer only
+//                   the candidates up to that bin.  mean_i = sum of the k smallest
 //                   sqrt(d^2) / k; then mu, sigma (Bessel) over points with mean_i > 0 and
 //                   keep_i = 0 < mean_i < mu + ratio * sigma — reduced in a fixed order.
 #include "b2_common.cuh"
@@ -85,6 +87,60 @@ radius_count_kernel(const float4* __restrict__ pts, int n, const CellEntry* __re
     if (lane == 0) keep[i] = inside > nb_points ? 1 : 0;
 }
 
+// Walk the (2m+1)^3 stencil of a point with the whole warp: cells are looked up 32 at a time, their points
+// are dealt to the lanes in stencil order, and fn(running_index, d2_bits, lane_is_live) is called for every
+// candidate — by all 32 lanes together (live == false for the padding lanes of the last trip), so fn may use
+// warp collectives.  Returns the number of candidates.
+template <typename Fn>
+__device__ __forceinline__ int sweep_stencil(int m, int cx, int cy, int cz, double Px, double Py, double Pz,
+                                             const CellEntry* __restrict__ entries, unsigned mask,
+                                             const float4* __restrict__ gpts, Fn&& fn) {
+    const int lane = threadIdx.x & 31;
+    const int side = 2 * m + 1;
+    const int ncell = side * side * side;
+    int total = 0;
+    for (int c0 = 0; c0 < ncell; c0 += 32) {
+        const int c = c0 + lane;
+        unsigned off = 0;
+        int cnt = 0;
+        if (c < ncell) {
+            const int nx = cx + c / (side * side) - m, ny = cy + (c / side) % side - m, nz = cz + c % side - m;
+            if (nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536) {
+                const unsigned long long key = pair_cell_key(0u, nx, ny, nz);
+                const CellEntry e = grid_lookup(entries, mask, key);
+                if (e.key == key) {
+                    off = e.off;
+                    cnt = (int)e.cnt;
+                }
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(kFull, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int sum = __shfl_sync(kFull, incl, 31);
+        const int excl = incl - cnt;
+        for (int t0 = 0; t0 < sum; t0 += 32) {
+            const int cnd = t0 + lane;
+            const int owner = warp_owner(incl, cnd);
+            const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
+            const int o_excl = __shfl_sync(kFull, excl, owner & 31);
+            const bool live = cnd < sum;
+            unsigned long long bits = 0;
+            if (live) {
+                const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
+                bits = (unsigned long long)__double_as_longlong(
+                    dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z));
+            }
+            fn(total + cnd, bits, live);
+        }
+        total += sum;
+    }
+    return total;
+}
+
 // k-nearest mean distance, one warp per point.
 __global__ void __launch_bounds__(kThreads)
 knn_mean_kernel(const float4* __restrict__ pts, int n, const CellEntry* __restrict__ entries, unsigned mask,
@@ -112,52 +168,77 @@ knn_mean_kernel(const float4* __restrict__ pts, int n, const CellEntry* __restri
         // a sparse neighbourhood is handed to the next, 4x coarser grid level instead of sweeping
         // ever larger shells of empty cells here (the coarsest level has max_ring = INT_MAX)
         if (m > max_ring) return;
-        const int side = 2 * m + 1;
-        const int ncell = side * side * side;
         // ---- gather the squared distances of every point in the (2m+1)^3 stencil -------------------
-        int total = 0;
-        for (int c0 = 0; c0 < ncell; c0 += 32) {
-            const int c = c0 + lane;
-            unsigned off = 0;
-            int cnt = 0;
-            if (c < ncell) {
-                const int nx = cx + c / (side * side) - m, ny = cy + (c / side) % side - m, nz = cz + c % side - m;
-                if (nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536) {
-                    const unsigned long long key = pair_cell_key(0u, nx, ny, nz);
-                    const CellEntry e = grid_lookup(entries, mask, key);
-                    if (e.key == key) {
-                        off = e.off;
-                        cnt = (int)e.cnt;
-                    }
-                }
-            }
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int v = __shfl_up_sync(kFull, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const int sum = __shfl_sync(kFull, incl, 31);
-            const int excl = incl - cnt;
-            for (int t0 = 0; t0 < sum; t0 += 32) {
-                const int cnd = t0 + lane;
-                const int owner = warp_owner(incl, cnd);
-                const unsigned o_off = __shfl_sync(kFull, off, owner & 31);
-                const int o_excl = __shfl_sync(kFull, excl, owner & 31);
-                if (cnd < sum && total + cnd < kBufCap) {
-                    const float4 t = __ldg(gpts + (o_off + (unsigned)(cnd - o_excl)));
-                    const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                    buf[total + cnd] = (unsigned long long)__double_as_longlong(d2);
-                }
-            }
-            total += sum;
-        }
+        int total = sweep_stencil(m, cx, cy, cz, Px, Py, Pz, entries, mask, gpts,
+                                  [&](int idx, unsigned long long bits, bool live) {
+                                      if (live && idx < kBufCap) buf[idx] = bits;
+                                  });
         const bool covers_all = m >= ext;
         if (total < k && !covers_all) continue;  // not enough candidates yet: next ring
         __syncwarp();
         const int kk0 = min(k, total);
+        bool buffered = total <= kBufCap;
+        if (!buffered) {
+            // ---- more candidates than the buffer holds (cell coarse for the local density): two more sweeps.
+            //      Sweep A histograms the distances on 1024 bins that are linear in d^2 (a surface-like
+            //      neighbourhood fills them evenly), which locates the bin of the k-th smallest; sweep B
+            //      buffers, in stencil order, only the candidates up to that bin — the k nearest plus a few.
+            unsigned* hist1k = reinterpret_cast<unsigned*>(buf);  // the overflowed buffer holds nothing of use
+            for (int b = lane; b < 1024; b += 32) hist1k[b] = 0;
+            __syncwarp();
+            const double reach1 = dmul((double)(m + 1), cell);
+            const double scale = 1024.0 / dmul(3.0, dmul(reach1, reach1));  // every candidate has d2 <= 3 reach1^2
+            auto bin_of = [&](unsigned long long bits) -> int {
+                const double v = __longlong_as_double((long long)bits) * scale;  // monotone in d2
+                return v >= 1023.0 ? 1023 : (int)v;
+            };
+            sweep_stencil(m, cx, cy, cz, Px, Py, Pz, entries, mask, gpts,
+                          [&](int, unsigned long long bits, bool live) {
+                              if (live) atomicAdd(&hist1k[bin_of(bits)], 1u);
+                          });
+            __syncwarp();
+            // lane l owns bins [32 l, 32 l + 32): find the bin where the running count reaches kk0
+            unsigned lsum = 0;
+            for (int b = 0; b < 32; ++b) lsum += hist1k[lane * 32 + b];
+            unsigned incl = lsum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned v = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const bool mine = incl - lsum < (unsigned)kk0 && (unsigned)kk0 <= incl;
+            int cut = 0, upto = 0;
+            if (mine) {
+                unsigned run = incl - lsum;
+                for (int b = 0; b < 32; ++b) {
+                    run += hist1k[lane * 32 + b];
+                    if (run >= (unsigned)kk0) {
+                        cut = lane * 32 + b;
+                        upto = (int)run;
+                        break;
+                    }
+                }
+            }
+            const int src = __ffs(__ballot_sync(kFull, mine)) - 1;
+            cut = __shfl_sync(kFull, cut, src);
+            upto = __shfl_sync(kFull, upto, src);  // candidates in bins <= cut
+            __syncwarp();
+            if (upto <= kBufCap) {
+                int filled = 0;
+                sweep_stencil(m, cx, cy, cz, Px, Py, Pz, entries, mask, gpts,
+                              [&](int, unsigned long long bits, bool live) {
+                                  const bool take = live && bin_of(bits) <= cut;
+                                  const unsigned votes = __ballot_sync(kFull, take);
+                                  if (take) buf[filled + __popc(votes & ((1u << lane) - 1u))] = bits;
+                                  filled += __popc(votes);
+                              });
+                total = filled;  // == upto: the k nearest are among them, in stencil order
+                buffered = true;
+                __syncwarp();
+            }
+        }
         unsigned long long kth = 0;  // bit pattern of the kk0-th smallest d^2
-        if (total <= kBufCap) {
+        if (buffered) {
             // ---- MSB radix select over the buffered bit patterns -------------------------------------
             unsigned long long prefix = 0;
             int want = kk0;  // 1-based rank among the elements matching the prefix
@@ -207,36 +288,15 @@ knn_mean_kernel(const float4* __restrict__ pts, int n, const CellEntry* __restri
             }
             kth = prefix;
         } else {
-            // ---- overflow (cell far too coarse for the local density): bisection on the bit pattern,
-            //      re-reading the stencil every step.  Slow, exact, and rare when the caller sizes the
-            //      cell from the cloud's density. -----------------------------------------------------
+            // ---- degenerate neighbourhood (more than the buffer holds inside ONE histogram bin, e.g. thousands
+            //      of coincident points): bisection on the bit pattern, one sweep per step.  Slow, exact. -----
             unsigned long long lo = 0, hi = 0x7ff0000000000000ull;
             while (lo < hi) {
                 const unsigned long long mid = lo + ((hi - lo) >> 1);
                 int cle = 0;
-                for (int c0 = 0; c0 < ncell; c0 += 32) {
-                    const int c = c0 + lane;
-                    unsigned off = 0;
-                    int cnt = 0;
-                    if (c < ncell) {
-                        const int nx = cx + c / (side * side) - m, ny = cy + (c / side) % side - m, nz = cz + c % side - m;
-                        if (nx >= 0 && nx < 65536 && ny >= 0 && ny < 65536 && nz >= 0 && nz < 65536) {
-                            const unsigned long long key = pair_cell_key(0u, nx, ny, nz);
-                            const CellEntry e = grid_lookup(entries, mask, key);
-                            if (e.key == key) {
-                                off = e.off;
-                                cnt = (int)e.cnt;
-                            }
-                        }
-                    }
-                    int local = 0;
-                    for (int j = 0; j < cnt; ++j) {
-                        const float4 t = __ldg(gpts + off + j);
-                        const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                        local += ((unsigned long long)__double_as_longlong(d2) <= mid) ? 1 : 0;
-                    }
-                    cle += __reduce_add_sync(kFull, local);
-                }
+                sweep_stencil(m, cx, cy, cz, Px, Py, Pz, entries, mask, gpts,
+                              [&](int, unsigned long long bits, bool live) { cle += (live && bits <= mid) ? 1 : 0; });
+                cle = __reduce_add_sync(kFull, cle);
                 if (cle >= kk0) hi = mid; else lo = mid + 1;
             }
             kth = lo;
@@ -247,7 +307,7 @@ knn_mean_kernel(const float4* __restrict__ pts, int n, const CellEntry* __restri
         // ---- mean of the k smallest distances (ties at the k-th all have the same length) ------------
         double s = 0.0;
         int clt = 0;
-        if (total <= kBufCap) {
+        if (buffered) {
             for (int e = lane; e < total; e += 32) {
                 const unsigned long long v = buf[e];
                 if (v < kth) {
@@ -256,23 +316,13 @@ knn_mean_kernel(const float4* __restrict__ pts, int n, const CellEntry* __restri
                 }
             }
         } else {
-            for (int c0 = 0; c0 < ncell; c0 += 32) {
-                const int c = c0 + lane;
-                if (c >= ncell) continue;
-                const int nx = cx + c / (side * side) - m, ny = cy + (c / side) % side - m, nz = cz + c % side - m;
-                if (nx < 0 || nx >= 65536 || ny < 0 || ny >= 65536 || nz < 0 || nz >= 65536) continue;
-                const unsigned long long key = pair_cell_key(0u, nx, ny, nz);
-                const CellEntry e = grid_lookup(entries, mask, key);
-                if (e.key != key) continue;
-                for (unsigned j = 0; j < e.cnt; ++j) {
-                    const float4 t = __ldg(gpts + e.off + j);
-                    const double d2 = dist2_strict(Px, Py, Pz, (double)t.x, (double)t.y, (double)t.z);
-                    if ((unsigned long long)__double_as_longlong(d2) < kth) {
-                        s += sqrt(d2);
-                        ++clt;
-                    }
-                }
-            }
+            sweep_stencil(m, cx, cy, cz, Px, Py, Pz, entries, mask, gpts,
+                          [&](int, unsigned long long bits, bool live) {
+                              if (live && bits < kth) {
+                                  s += sqrt(__longlong_as_double((long long)bits));
+                                  ++clt;
+                              }
+                          });
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
