@@ -190,8 +190,8 @@ class Engine:
         self._check(self.lib.b2_synchronize(self.h))
 
     def set_icp_driver(self, driver) -> None:
-        """'auto' | 'group' | 'sweep' (or 0/1/2): the kernel that runs ICP steps on pair / slab grids."""
-        code = {"auto": 0, "group": 1, "sweep": 2}.get(driver, driver)
+        """'auto' | 'group' | 'sweep' | 'sweep4' (or 0..3): the kernel that runs ICP steps on pair / slab grids."""
+        code = {"auto": 0, "group": 1, "sweep": 2, "sweep4": 3}.get(driver, driver)
         self._check(self.lib.b2_set_icp_driver(self.h, int(code)))
 
     def launch_count(self) -> int:

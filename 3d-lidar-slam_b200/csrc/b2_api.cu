@@ -322,7 +322,7 @@ int b2_synchronize(b2_handle h) {
 
 int b2_set_icp_driver(b2_handle h, int driver) {
     CTX(h);
-    if (driver < B2_ICP_DRIVER_AUTO || driver > B2_ICP_DRIVER_SWEEP)
+    if (driver < B2_ICP_DRIVER_AUTO || driver > B2_ICP_DRIVER_SWEEP4)
         return set_error(c, B2_ERR_INVALID, "b2_set_icp_driver: unknown driver %d", driver);
     c->icp_driver = driver;
     return B2_OK;

@@ -91,7 +91,7 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                        search_only, loop_handle);
 }
 
-template <int MODE, int KIND>
+template <int MODE, int KIND, int L>
 void launch_sweep(Context* c, dim3 grid, const float4* src, const int* src_offs, const int* ns_dev, int ns_max,
                   const GridView& g, const float4* nrm, const int* tgt_offs, const IcpParams& prm, IcpState* st,
                   double* partial, int* tickets, IcpResultDev* res, int* corr, int* ndone, double* d2_out,
@@ -108,7 +108,7 @@ void launch_sweep(Context* c, dim3 grid, const float4* src, const int* src_offs,
     static const bool no_pdl = getenv("B2_NO_PDL") != nullptr;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    cudaLaunchKernelEx(&cfg, icp_sweep_kernel<MODE, KIND>, src, src_offs, ns_dev, ns_max, (const CellEntry*)g.entries,
+    cudaLaunchKernelEx(&cfg, icp_sweep_kernel<MODE, KIND, L>, src, src_offs, ns_dev, ns_max, (const CellEntry*)g.entries,
                        g.mask, (const float4*)g.pts, (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets,
                        res, corr, ndone, d2_out, search_only);
 }
@@ -206,10 +206,14 @@ int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max,
 // The sweep kernels keep one accumulator column per thread in dynamic shared memory (> 48 KB): opt in once
 // per context (device attribute, not a stream operation — done at creation so it never lands in a capture).
 int icp_configure(Context* c) {
-    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
-    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
-    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
-    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+    B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
     return B2_OK;
 }
 
@@ -247,8 +251,16 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     // not fill the machine and latency is the cost) and the thread-per-query sweep (pruned walk: best when
     // they do).  b2_set_icp_driver forces one (parity tests run both; results are identical).
     bool sweep = grid.is_map != 2 && (long long)ns_max >= kSweepMinQueries;
-    if (c->icp_driver != 0 && grid.is_map != 2) sweep = c->icp_driver == 2;
-    const int gx = icp_grid_x(ns_max, n_pairs, sweep ? grid.is_map : 2);
+    int sweep_lanes = 1;  // lanes per query of the sweep kernel: 4 when a small problem has to fill the machine
+    if (c->icp_driver != 0 && grid.is_map != 2) {
+        sweep = c->icp_driver >= 2;
+        sweep_lanes = c->icp_driver == 3 ? 4 : 1;
+    }
+    int gx = icp_grid_x(ns_max, n_pairs, sweep ? grid.is_map : 2);
+    if (sweep && sweep_lanes == 4 && n_pairs == 1) {  // one 8-query block per warp before any warp gets a second one
+        gx = div_up(ns_max, 8);
+        if (gx > kCtasPerSm * kSMs) gx = kCtasPerSm * kSMs;
+    }
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
     B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs);
     B2_WS(c, tickets, int, WS_ICP_TICKET, sizeof(int) * ((size_t)n_pairs + 1));
@@ -314,8 +326,14 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     launch_iter<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
                       tickets, results_dev, corr_out, ndone, d2_out, search_only, launch_stream, loop_handle)
 #define B2_ICP_SWEEP(M, K)                                                                                     \
-    launch_sweep<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
-                       tickets, results_dev, corr_out, ndone, d2_out, search_only)
+    do {                                                                                                       \
+        if (sweep_lanes == 4)                                                                                  \
+            launch_sweep<M, K, 4>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, \
+                                  partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);       \
+        else                                                                                                   \
+            launch_sweep<M, K, 1>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, \
+                                  partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);       \
+    } while (0)
         if (prm.mode == 0) {
             if (grid.is_map == 2) B2_ICP_LAUNCH(0, 2);
             else if (!sweep && grid.is_map == 1) B2_ICP_LAUNCH(0, 1);
@@ -387,12 +405,15 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
                 if (h[8 + 2 * b + 1] < tmain_min) tmain_min = h[8 + 2 * b + 1];
                 if (h[8 + 2 * b + 1] > tmain_max) tmain_max = h[8 + 2 * b + 1];
             }
+            fprintf(stderr, "[b2 blocks start-minus-t0 ns]");
+            for (int b = 0; b < gx && b < 1024; ++b) fprintf(stderr, " %llu", h[8 + 2 * b] - t0);
+            fprintf(stderr, "\n");
             fprintf(stderr, "[b2 blocks main-done-minus-start ns]");
             for (int b = 0; b < gx && b < 1024; ++b) fprintf(stderr, " %llu", h[8 + 2 * b + 1] - h[8 + 2 * b]);
             fprintf(stderr, "\n");
             fprintf(stderr, "[b2 tail] last launch (ns from first CTA start): last CTA start %llu | main done min %llu max %llu | "
-                            "last-CTA: ticket won %llu, reduced %llu, step done %llu\n",
-                    tstart_max - t0, tmain_min - t0, tmain_max - t0, h[0] - t0, h[1] - t0, h[2] - t0);
+                            "last-CTA: ticket won %llu, reduced %llu, step done %llu | (sweep) fold start %llu, folded %llu, fenced %llu\n",
+                    tstart_max - t0, tmain_min - t0, tmain_max - t0, h[0] - t0, h[1] - t0, h[2] - t0, h[3] - t0, h[4] - t0, h[5] - t0);
         }
 #endif
         for (auto& e : evs) cudaEventDestroy(e);

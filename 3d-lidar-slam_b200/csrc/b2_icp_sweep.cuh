@@ -43,12 +43,16 @@ struct SweepCfg {  // threads per sweep CTA (one CTA per SM): the register budge
     static constexpr size_t kSmem = sizeof(double) * kNT * kT;  // one accumulator column per thread
 };
 
-template <int MODE, int KIND>
+// L = lanes of a warp per query: 1 for batches (32 queries per warp round); 4 when one pair has to fill the
+// machine (8 queries per round: the lanes of a group share the screening of the query's own cell, and the
+// three that hold no query are extra hands for the pooled neighbour tasks).
+template <int MODE, int KIND, int L>
 __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __restrict__ sT,
                                            const double* __restrict__ sPivot, const GridMeta& meta, float4 p, bool valid,
                                            int q, double* __restrict__ acc, unsigned long long* __restrict__ wbest,
                                            unsigned* __restrict__ wsecond) {
-    // (warp-collective: all 32 lanes enter; `valid` marks the lanes that hold a query)
+    // (warp-collective: all 32 lanes enter; `valid` marks the lanes that hold a query — with L > 1 only the
+    // first lane of a group can)
     const int lane = threadIdx.x & 31;
     const D3 P = xform_strict(sT, (double)p.x, (double)p.y, (double)p.z);
     const double Px = P.x, Py = P.y, Pz = P.z;
@@ -109,9 +113,10 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
     unsigned bpos = 0;
     float ub = (float)a.r2 * 1.00001f;  // nothing at or beyond the radius can be a correspondence
     // float32 screening of the points [off, off + cnt) for a query at (x, y, z): running best two
-    auto screen_cell = [&](unsigned off, int cnt, float x, float y, float z, float& b1, float& b2, unsigned& bp) {
+    auto screen_cell = [&](unsigned off, int cnt, float x, float y, float z, float& b1, float& b2, unsigned& bp,
+                           int first, int stride) {
         const float4* cp = a.gpts + off;
-        for (int j = 0; j < cnt; ++j) {
+        for (int j = first; j < cnt; j += stride) {
             const float4 t = __ldg(cp + j);
             const float fx = x - t.x, fy = y - t.y, fz = z - t.z;
             const float d = fx * fx + fy * fy + fz * fz;
@@ -122,17 +127,54 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
     };
     unsigned m = 0;  // this query's list: bit b = walk position b can still hold a closer point
     float xm = 0.f, xp = 0.f, ym = 0.f, yp = 0.f, zm = 0.f, zp = 0.f;
-    if (searching) {
-        {  // the query's own cell first: it usually holds the neighbour and gives the bound for the rest
+    // merge (d2, position) of one screened share into the slot of its query: an atomic min keeps the best,
+    // whatever loses goes to the second best (non-negative floats order like their bit patterns)
+    auto merge_into = [&](int slot, float l1, float l2, unsigned lp) {
+        const unsigned long long mine = ((unsigned long long)__float_as_uint(l1) << 32) | lp;
+        const unsigned long long old = atomicMin(wbest + slot, mine);
+        const unsigned loser = mine < old ? (unsigned)(old >> 32) : __float_as_uint(l1);
+        atomicMin(wsecond + slot, min(loser, __float_as_uint(l2)));
+    };
+    // the query's own cell first: it usually holds the neighbour and gives the bound for the rest
+    if (L == 1) {
+        if (searching) {
             bool ok = true;
             const unsigned long long key = key_of(offset_code(0, 0, 0), ok);
             unsigned off;
             int cnt;
-            if (ok && probe(key, off, cnt)) {
-                screen_cell(off, cnt, Pxf, Pyf, Pzf, bf, sf, bpos);
-                if (bf < INFINITY) ub = fminf(ub, (bf + 2.0f * margin(bf)) * 1.00001f);  // true d2 <= bf + M
-            }
+            if (ok && probe(key, off, cnt)) screen_cell(off, cnt, Pxf, Pyf, Pzf, bf, sf, bpos, 0, 1);
         }
+    } else {
+        // the L lanes of the group screen the cell together: lane s takes points s, s + L, ...
+        const int lead = lane & ~(L - 1);
+        bool ok = searching;
+        unsigned long long key = 0;
+        if (searching) key = key_of(offset_code(0, 0, 0), ok);
+        ok = __shfl_sync(kFull, ok, lead);
+        key = __shfl_sync(kFull, key, lead);
+        const float gx = __shfl_sync(kFull, Pxf, lead), gy = __shfl_sync(kFull, Pyf, lead), gz = __shfl_sync(kFull, Pzf, lead);
+        wbest[lane] = 0x7f80000000000000ull;  // (+inf, position 0)
+        wsecond[lane] = 0x7f800000u;
+        __syncwarp();
+        unsigned off;
+        int cnt;
+        if (ok && probe(key, off, cnt)) {
+            float l1 = INFINITY, l2 = INFINITY;
+            unsigned lp = 0;
+            screen_cell(off, cnt, gx, gy, gz, l1, l2, lp, lane - lead, L);
+            if (l1 < INFINITY) merge_into(lead, l1, l2, lp);
+        }
+        __syncwarp();
+        if (searching) {
+            const unsigned long long w = wbest[lane];
+            bf = __uint_as_float((unsigned)(w >> 32));
+            bpos = (unsigned)w;
+            sf = __uint_as_float(wsecond[lane]);
+        }
+        __syncwarp();
+    }
+    if (searching) {
+        if (bf < INFINITY) ub = fminf(ub, (bf + 2.0f * margin(bf)) * 1.00001f);  // true d2 <= bf + M
         // conservative (too small) squared distance from the query to the slab of cells at -1 / +1 per axis
         auto sq = [](float v) { return v * v * 0.9999f; };
         xm = sq(fmaxf(ax - slack, 0.f)); xp = sq(fmaxf(E - ax - slack, 0.f));
@@ -192,14 +234,8 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
             if (probe(okb + key_delta(a.walk[b]), off, cnt)) {
                 float l1 = INFINITY, l2 = INFINITY;
                 unsigned lp = 0;
-                screen_cell(off, cnt, ox, oy, oz, l1, l2, lp);
-                if (l1 < INFINITY) {
-                    const unsigned long long mine = ((unsigned long long)__float_as_uint(l1) << 32) | lp;
-                    const unsigned long long old = atomicMin(wbest + o, mine);
-                    // non-negative floats order like their bit patterns
-                    const unsigned loser = mine < old ? (unsigned)(old >> 32) : __float_as_uint(l1);
-                    atomicMin(wsecond + o, min(loser, __float_as_uint(l2)));
-                }
+                screen_cell(off, cnt, ox, oy, oz, l1, l2, lp, 0, 1);
+                if (l1 < INFINITY) merge_into(o, l1, l2, lp);
             }
         }
     }
@@ -220,7 +256,7 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
             const unsigned long long key = key_of(a.walk[b], ok);
             unsigned off;
             int cnt;
-            if (ok && probe(key, off, cnt)) screen_cell(off, cnt, Pxf, Pyf, Pzf, bf, sf, bpos);
+            if (ok && probe(key, off, cnt)) screen_cell(off, cnt, Pxf, Pyf, Pzf, bf, sf, bpos, 0, 1);
         }
     }
     if (!valid) return;
@@ -295,7 +331,7 @@ __device__ __forceinline__ void search_one(const SearchArgs& a, const double* __
     }
 }
 
-template <int MODE, int KIND>  // KIND 0: pair grid, 1: resident map with slabs
+template <int MODE, int KIND, int L>  // KIND 0: pair grid, 1: resident map with slabs; L: lanes per query
 __global__ void __launch_bounds__(SweepCfg<MODE>::kT, 1)
 icp_sweep_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs, const int* __restrict__ ns_dev,
                  int ns_max, const CellEntry* __restrict__ entries, unsigned mask, const float4* __restrict__ gpts,
@@ -316,6 +352,7 @@ icp_sweep_kernel(const float4* __restrict__ src, const int* __restrict__ src_off
     __shared__ double sSum[kTerms];
     __shared__ int sLast;
 
+    B2_TS_BLOCK(0);
     asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(GridMeta) / 8)
         reinterpret_cast<double*>(&sMeta)[threadIdx.x - 32] =
@@ -345,32 +382,40 @@ icp_sweep_kernel(const float4* __restrict__ src, const int* __restrict__ src_off
     a.r2 = dmul(prm.max_corr, prm.max_corr);
     a.corr_out = corr_out; a.d2_out = d2_out; a.search_only = search_only;
 
-    // 32-query blocks are dealt to the warps round-robin over (round, warp, CTA), so that a source smaller
+    // blocks of Q queries are dealt to the warps round-robin over (round, warp, CTA), so that a source smaller
     // than the grid still spreads over every SM
     const int lane = threadIdx.x & 31;
     const int warps_total = gridDim.x * (kT / 32);
-    for (int blk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; sb + blk * 32 < se; blk += warps_total) {
-        const int q = sb + blk * 32 + lane;
-        const bool valid = q < se;
+    constexpr int Q = 32 / L;  // queries of a warp round
+    for (int blk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; sb + blk * Q < se; blk += warps_total) {
+        const int q = sb + blk * Q + lane / L;
+        const bool valid = (lane % L) == 0 && q < se;
         const float4 p = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        search_one<MODE, KIND>(a, sState.T, sState.pivot, sMeta, p, valid, q, sAcc + threadIdx.x,
-                               sBest + (threadIdx.x & ~31), sSecond + (threadIdx.x & ~31));
+        search_one<MODE, KIND, L>(a, sState.T, sState.pivot, sMeta, p, valid, q, sAcc + threadIdx.x,
+                                  sBest + (threadIdx.x & ~31), sSecond + (threadIdx.x & ~31));
     }
     if (search_only) return;
 
     __syncthreads();
+    B2_TS_BLOCK(1);
+    B2_TS(3);
     cta_fold<NT, kT>(sAcc, partial + ((size_t)pair * gridDim.x + blockIdx.x) * kTerms);
     __syncthreads();
+    B2_TS(4);
     if (threadIdx.x == 0) {
         __threadfence();
+        B2_TS(5);
         int t = atomicAdd(&tickets[pair], 1);
         sLast = (t == (int)gridDim.x - 1);
     }
     __syncthreads();
     if (!sLast) return;
+    B2_TS(0);
     grid_fold<NT>(partial + (size_t)pair * gridDim.x * kTerms, (int)gridDim.x, sRed, sSum);
+    B2_TS(1);
     if (threadIdx.x == 0) {
         tickets[pair] = 0;
         icp_step<MODE>(sSum, se - sb, prm, sState, st, results + pair, ndone);
     }
+    B2_TS(2);
 }

@@ -74,6 +74,7 @@ unsigned long long b2_launch_count(b2_handle h);
 #define B2_ICP_DRIVER_AUTO 0
 #define B2_ICP_DRIVER_GROUP 1
 #define B2_ICP_DRIVER_SWEEP 2
+#define B2_ICP_DRIVER_SWEEP4 3 /* the sweep kernel with four lanes per query (small problems) */
 int b2_set_icp_driver(b2_handle h, int driver);
 
 /* ---- layout helpers ----------------------------------------------------- */

@@ -42,10 +42,10 @@ def engine(b2):
     eng.close()
 
 
-@pytest.fixture(params=["group", "sweep"])
+@pytest.fixture(params=["group", "sweep", "sweep4"])
 def driver(request, engine):
     """Run a test under both ICP-step kernels of the pair / slab grids (include/b2slam.h B2_ICP_DRIVER_*):
-    the 4-lane-group kernel and the thread-per-query sweep must give identical results."""
+    the 4-lane-group kernel and the sweep kernel (one or four lanes per query) must give identical results."""
     engine.set_icp_driver(request.param)
     yield request.param
     engine.set_icp_driver("auto")
