@@ -85,10 +85,11 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
     static const bool no_pdl = getenv("B2_NO_PDL") != nullptr;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
+    static const int spread_partial = getenv("B2_SPREAD_PARTIAL") ? atoi(getenv("B2_SPREAD_PARTIAL")) : 0;  // experiment
     cudaLaunchKernelEx(&cfg, icp_iter_kernel<MODE, IS_MAP>, src, src_offs, ns_dev, ns_max,
                        (const CellEntry*)g.entries, g.mask, (const float4*)g.pts, (const VoxEntry*)g.vox,
                        (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets, res, corr, ndone, d2_out,
-                       search_only, loop_handle);
+                       search_only, loop_handle, spread_partial);
 }
 
 template <int MODE, int KIND, int L>

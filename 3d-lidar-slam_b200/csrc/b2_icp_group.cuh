@@ -338,7 +338,7 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
                 const int* __restrict__ tgt_offs, IcpParams prm, IcpState* __restrict__ states,
                 double* __restrict__ partial, int* __restrict__ tickets, IcpResultDev* __restrict__ results,
                 int* __restrict__ corr_out, int* __restrict__ ndone, double* __restrict__ d2_out,
-                int search_only, unsigned long long loop_handle) {
+                int search_only, unsigned long long loop_handle, int spread_partial) {
     constexpr int NT = MODE == 0 ? 17 : 29;  // live accumulator terms
     const int pair = blockIdx.y;
     IcpState* st = states + pair;
@@ -398,15 +398,31 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     a.r2 = dmul(prm.max_corr, prm.max_corr);
     a.corr_out = corr_out; a.d2_out = d2_out; a.search_only = search_only;
 
-    // queries are dealt to groups round-robin over (round, CTA, group)
+    // Queries are dealt to groups round-robin over (round, CTA, group): a CTA works on 160 consecutive queries per
+    // round (neighbours in space: its warps share L1 lines).  When the source needs more than one round, the LAST,
+    // partial round is dealt in 8-query warp chunks round-robin over the CTAs instead, so that every SM gets an
+    // equal share of it rather than the first CTAs a full extra round (config 1: 29.8 k queries = 1.26 rounds).
+    const int full_rounds = (se - sb) / groups_total;
+    const bool spread = full_rounds >= 1 || spread_partial;
     bool first = !src_offs;
-    for (int q0 = sb + warp_first; q0 < se; q0 += groups_total) {  // warp-uniform trip count
+    const int q_end = spread ? sb + full_rounds * groups_total : se;
+    for (int q0 = sb + warp_first; q0 < q_end; q0 += groups_total) {  // warp-uniform trip count
         const int q = q0 + lane / kGroup;
-        const bool valid = q < se;
+        const bool valid = q < q_end;
         float4 p = p_first;
         if (!first && (lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
         first = false;
         search_round<MODE, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+    }
+    if (spread) {
+        const int q0 = q_end + ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * (32 / kGroup);
+        if (q0 < se) {  // (at most one chunk per warp: the partial round holds fewer than gridDim.x * 20 chunks)
+            const int q = q0 + lane / kGroup;
+            const bool valid = q < se;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
+            search_round<MODE, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+        }
     }
     if (search_only) return;
 
