@@ -436,6 +436,12 @@ def cpu_reference_run(n_scans: int, scene_seed: int, map_points_target: int = 2_
     from oracle import cpu as orc
     from oracle import pipeline
 
+    # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun exports 1)
+    try:
+        host_threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        host_threads = os.cpu_count() or 1
+    orc.set_num_threads(host_threads)
     scene = synth.make_corridor_scene(scene_seed, length=CORRIDOR_LEN)
     # raw map of ~2 M points around the trajectory start (the reference's map is raw points, not voxels)
     span = 28.0
