@@ -71,9 +71,10 @@ def test_loop_registers_every_scan_in_order_and_exports_once_per_batch():
     stop, reset = multiprocessing.Event(), multiprocessing.Event()
     loop = ProcessLoop(proc, dt, stop, reset, max_batch=16, idle_timeout=0.02)
     th = threading.Thread(target=loop.run, daemon=True)
-    th.start()
-    for i in range(100):
+    for i in range(100):  # a backlog, as after a burst from the subscriber
         dt.pixel_depth_map_queue.put(np.array([i, 0, 0], np.float32))
+    time.sleep(0.3)  # let the queue's feeder thread flush the backlog into the pipe
+    th.start()
     assert _wait(lambda: loop.scans_processed == 100)
     assert proc.seen == list(range(100))
     assert proc.exports == loop.batches <= 100  # one map materialisation per batch, not per scan
