@@ -69,6 +69,9 @@ bbox_kernel(const float4* __restrict__ pts, const int* __restrict__ offs, const 
         if (T) q = xform_strict(Tl, q.x, q.y, q.z);
         mn[0] = fmin(mn[0], q.x); mn[1] = fmin(mn[1], q.y); mn[2] = fmin(mn[2], q.z);
         mx[0] = fmax(mx[0], q.x); mx[1] = fmax(mx[1], q.y); mx[2] = fmax(mx[2], q.z);
+        // fmin / fmax skip NaN: a point without a voxel must not slip through — open the box to infinity, which
+        // prep_kernel reports as B2_ERR_KEY_RANGE (Open3D's int32 voxel index is undefined for it as well)
+        if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) mn[0] = -INFINITY;
     }
     __shared__ double smn[kBlock / 32][3], smx[kBlock / 32][3];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

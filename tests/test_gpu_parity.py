@@ -610,3 +610,25 @@ def test_batch_normals_and_point_to_plane_match_per_pair_oracle(engine, b2, driv
     with pytest.raises(b2.B2Error, match="normal_radius"):
         engine.icp_batch(engine.pack(np.concatenate(srcs)), torch.from_numpy(so).cuda(), T4,
                          torch.from_numpy(to).cuda(), prm, ds_voxel=0.02)
+
+
+def test_non_finite_points_fail_loudly_and_do_not_poison_the_engine(engine, b2, pair0):
+    """A NaN / Inf coordinate has no voxel (Open3D's int32 voxel index is undefined for it): the call must
+    raise, not hang or return garbage, and the engine must stay usable."""
+    src, tgt, _ = pair0
+    for bad in (np.nan, np.inf, -np.inf, 3e38):
+        pts = src[:5000].copy()
+        pts[1234, 1] = bad
+        with pytest.raises(b2.B2Error):
+            engine.voxel_downsample(engine.pack(pts), 0.02)
+        with pytest.raises(b2.B2Error):  # a target cannot be gridded either
+            engine.icp(engine.pack(src[:5000].copy()), engine.pack(pts), b2.make_params(0.05, 3))
+        # a non-finite SOURCE point simply has no correspondence
+        idx, _ = engine.nn_search(engine.pack(pts), engine.pack(tgt), 0.05)
+        oidx, _ = orc.nn_search(f64(np.delete(pts, 1234, axis=0)), f64(tgt), 0.05)
+        got = idx.cpu().numpy()
+        assert got[1234] == -1
+        np.testing.assert_array_equal(np.delete(got, 1234), oidx)
+    cent, keys = engine.voxel_downsample(engine.pack(src), 0.02)  # still fine afterwards
+    oc, ok, on = orc.voxel_downsample(f64(src), 0.02)
+    np.testing.assert_array_equal(keys.cpu().numpy(), ok)
