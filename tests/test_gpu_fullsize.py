@@ -60,3 +60,39 @@ def test_full_size_scan_to_map_registration(engine, b2, big_map):
     engine.map_fuse(engine.pack(scan), res.matrix())
     after = engine.map_size()
     assert before <= after < before + 3000  # a registered scan lands almost entirely in existing voxels
+
+
+def test_large_batch_takes_the_sweep_driver_and_agrees_with_single_pair_runs(engine, b2):
+    """16 full-size pairs (~470 k queries) make the automatic driver choice pick the thread-per-query sweep
+    kernel with several CTAs per pair.  Size-independent properties: duplicated pairs give bit-identical
+    records wherever they sit in the batch, and every record equals the single-pair registration of the same
+    clouds (which runs the 4-lane-group kernel): same iterations, same fitness, transform within tolerance."""
+    import torch
+    from conftest import assert_transform_close
+    from lidar_slam_b200 import synth
+
+    distinct = [synth.make_pair(s) for s in (20, 21, 22, 23)]
+    order = [0, 1, 2, 3, 3, 2, 1, 0, 0, 0, 1, 1, 2, 2, 3, 3]
+    srcs = [distinct[i][0].numpy() for i in order]
+    tgts = [distinct[i][1].numpy() for i in order]
+    n = len(srcs[0])
+    offs = torch.arange(0, len(order) + 1, dtype=torch.int32, device="cuda") * n
+    prm = b2.make_params(0.05, 30)
+    res = engine.icp_batch(engine.pack(np.concatenate(srcs)), offs, engine.pack(np.concatenate(tgts)), offs, prm,
+                           ds_voxel=0.02)
+    engine.synchronize()
+    rec = b2.results_to_numpy(res)
+    first = {}
+    for pos, i in enumerate(order):
+        if i in first:
+            assert rec[pos].tobytes() == rec[first[i]].tobytes(), (pos, i)
+        else:
+            first[i] = pos
+    for i, pos in first.items():
+        sd, _ = engine.voxel_downsample(engine.pack(srcs[pos]), 0.02, want_keys=False)
+        td, _ = engine.voxel_downsample(engine.pack(tgts[pos]), 0.02, want_keys=False)
+        single, _ = engine.icp(sd, td, prm)
+        assert rec["iterations"][pos] == single.iterations
+        assert rec["fitness"][pos] == single.fitness
+        assert rec["n_correspondences"][pos] == single.n_correspondences
+        assert_transform_close(rec["transformation"][pos], single.matrix())
