@@ -26,7 +26,7 @@ EXPORTS = [
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
     "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results", "b2_icp_batch_p2l",
-    "b2_estimate_normals_batch",
+    "b2_estimate_normals_batch", "b2_map_export_records", "b2_map_merge_records",
 ]
 
 
@@ -87,6 +87,8 @@ def load():
         "b2_map_fuse": [vp, vp, i32, pd],
         "b2_map_size": [vp, C.POINTER(i64)],
         "b2_map_export": [vp, vp, vp, i64, C.POINTER(i64)],
+        "b2_map_export_records": [vp, vp, vp, i64, C.POINTER(i64)],
+        "b2_map_merge_records": [vp, vp, vp, i64],
         "b2_map_icp": [vp, vp, i32, pd, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan_dev": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
@@ -367,6 +369,27 @@ class Engine:
                                                C.byref(m)))
         return out[:m.value], (keys[:m.value] if want_keys else None)
 
+    def map_export_records(self):
+        """The map as mergeable records in canonical key order -> (keys int32 [m,3], sums float64 [m,4] =
+        (sum x, sum y, sum z, count)) — what ranks exchange when partial maps are gathered."""
+        torch = self.torch
+        n = self.map_size()
+        keys = self.empty((n, 3), torch.int32)
+        sums = self.empty((n, 4), torch.float64)
+        m = C.c_longlong(0)
+        if n:
+            self._check(self.lib.b2_map_export_records(self.h, keys.data_ptr(), sums.data_ptr(), n, C.byref(m)))
+        return keys[:m.value], sums[:m.value]
+
+    def map_merge_records(self, keys, sums):
+        """Add exported voxel records (unique keys) to the resident map, weighted by their counts."""
+        torch = self.torch
+        if not (keys.is_cuda and sums.is_cuda and keys.dtype == torch.int32 and sums.dtype == torch.float64
+                and keys.is_contiguous() and sums.is_contiguous() and keys.shape[0] == sums.shape[0]):
+            raise ValueError("expected contiguous CUDA int32 [n,3] keys and float64 [n,4] sums")
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self._check(self.lib.b2_map_merge_records(self.h, keys.data_ptr(), sums.data_ptr(), keys.shape[0]))
+
     def map_icp(self, src, params: IcpParams, init=None) -> IcpResult:
         src = self._pts(src)
         _i, ip = _dptr(init)
@@ -427,11 +450,16 @@ class Engine:
 
     # -- batch ----------------------------------------------------------------
     def icp_batch(self, src, src_offsets, tgt, tgt_offsets, params: IcpParams, ds_voxel: float = 0.0, init=None,
-                  normal_radius: float = 0.0, normal_max_nn: int = 20):
+                  normal_radius: float = 0.0, normal_max_nn: int = 20, sync: bool = True):
         """src/tgt: CUDA float32 [sum,4]; offsets: CUDA int32 [n_pairs+1].
         -> CUDA uint8 tensor viewable as RESULT_DTYPE records (stays on the device for NCCL gathers).
         ``params.mode == P2L``: the normals of every (down-sampled) target are estimated first with
-        (``normal_radius``, ``normal_max_nn``)."""
+        (``normal_radius``, ``normal_max_nn``).
+
+        The C call only enqueues the batch on the engine's stream.  ``sync=True`` (default) waits for it and
+        raises device-side failures here; with ``sync=False`` the caller's current stream is ordered after the
+        engine's stream (so ``.cpu()`` or a collective on it sees finished records) and failures surface at the
+        next ``synchronize()``."""
         torch = self.torch
         src, tgt = self._pts(src), self._pts(tgt)
         n_pairs = src_offsets.numel() - 1
@@ -447,6 +475,10 @@ class Engine:
             self._check(self.lib.b2_icp_batch(self.h, src.data_ptr(), src_offsets.data_ptr(), src.shape[0],
                                               tgt.data_ptr(), tgt_offsets.data_ptr(), tgt.shape[0], n_pairs,
                                               float(ds_voxel), ip, C.byref(params), res.data_ptr()))
+        if sync:
+            self.synchronize()
+        else:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return res
 
     def estimate_normals_batch(self, pts, offsets, radius: float, max_nn: int):

@@ -9,7 +9,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2slam.so")
-SOURCES = ["b2_sort.cu", "b2_voxel.cu", "b2_voxel_cluster.cu", "b2_grid.cu", "b2_icp.cu", "b2_normals.cu", "b2_filters.cu", "b2_map.cu", "b2_api.cu"]
+SOURCES = ["b2_sort.cu", "b2_voxel.cu", "b2_grid.cu", "b2_icp.cu", "b2_normals.cu", "b2_filters.cu", "b2_map.cu", "b2_api.cu"]
+# Measured-and-rejected variants (single-launch cluster voxel sort, persistent cooperative ICP kernel, the
+# four-lanes-per-query sweep driver) stay in the tree as documented experiments but are only compiled into the
+# library with B2_EXPERIMENTS=1; the default library and the default test matrix carry what ships.
+EXPERIMENT_SOURCES = ["b2_voxel_cluster.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
@@ -23,8 +27,16 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def _experiments() -> bool:
+    return os.environ.get("B2_EXPERIMENTS", "0") not in ("", "0")
+
+
 def _stale() -> bool:
     if not os.path.exists(OUT):
+        return True
+    flag = os.path.join(HERE, "build", "flavour.txt")
+    want = "experiments" if _experiments() else "default"
+    if not os.path.exists(flag) or open(flag).read().strip() != want:
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b2slam.h")]
@@ -41,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        extra = os.environ.get("B2_EXTRA_NVCC_FLAGS", "").split()
+        extra = os.environ.get("B2_EXTRA_NVCC_FLAGS", "").split() + (["-DB2_EXPERIMENTS"] if _experiments() else [])
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -50,12 +62,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr, file=sys.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
+    sources = SOURCES + (EXPERIMENT_SOURCES if _experiments() else [])
+    with ThreadPoolExecutor(max_workers=min(8, len(sources))) as ex:
+        objs = list(ex.map(compile_one, sources))
     cmd =[nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(os.path.join(objdir, "flavour.txt"), "w") as f:
+        f.write("experiments" if _experiments() else "default")
     return OUT
 
 

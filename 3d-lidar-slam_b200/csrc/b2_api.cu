@@ -128,7 +128,12 @@ __global__ void transform_kernel(const float4* __restrict__ in, int n, const dou
     out[i] = make_float4((float)q.x, (float)q.y, (float)q.z, p.w);
 }
 
-__global__ void copy_pose_kernel(const IcpResultDev* __restrict__ res, double* __restrict__ pose) {
+// Commit of a scan step: the registered pose becomes the prior of the next scan — unless the step failed on
+// the device (sticky status word: a sort beyond its pass budget, a full map), in which case neither the pose
+// nor the map (the merge kernels test the same word) is touched and the host can retry the scan.
+__global__ void copy_pose_kernel(const IcpResultDev* __restrict__ res, double* __restrict__ pose,
+                                 const int* __restrict__ dev_status) {
+    if (*dev_status != 0) return;
     if (threadIdx.x < 16) pose[threadIdx.x] = res->T[threadIdx.x];
 }
 
@@ -231,7 +236,13 @@ static_assert(sizeof(b2_icp_result) == sizeof(IcpResultDev), "result layouts mus
 
 extern "C" {
 
-const char* b2_version(void) { return "b2slam 0.1 (sm_100a)"; }
+const char* b2_version(void) {
+#ifdef B2_EXPERIMENTS
+    return "b2slam 0.2 (sm_100a) +experiments";
+#else
+    return "b2slam 0.2 (sm_100a)";
+#endif
+}
 
 int b2_create(int device, b2_handle* out) {
     if (!out) return B2_ERR_INVALID;
@@ -254,7 +265,10 @@ int b2_create(int device, b2_handle* out) {
         return B2_ERR_CUDA;
     }
     bool aux_ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaHostAlloc(&c->result_ring, sizeof(IcpResultDev) * kResultRing, cudaHostAllocDefault) == cudaSuccess;
+                  cudaHostAlloc(&c->result_ring, sizeof(IcpResultDev) * kResultRing, cudaHostAllocDefault) == cudaSuccess &&
+                  cudaHostAlloc((void**)&c->count_ring, sizeof(int) * kResultRing, cudaHostAllocDefault) == cudaSuccess;
+    for (int i = 0; i < 4 && aux_ok; ++i)
+        aux_ok = cudaEventCreateWithFlags(&c->ev_block[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && aux_ok; ++i)
         aux_ok = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -262,6 +276,9 @@ int b2_create(int device, b2_handle* out) {
     if (!aux_ok || icp_configure(c) != B2_OK) {
         delete[] c->ring_first;
         if (c->result_ring) cudaFreeHost(c->result_ring);
+        if (c->count_ring) cudaFreeHost(c->count_ring);
+        for (int i = 0; i < 4; ++i)
+            if (c->ev_block[i]) cudaEventDestroy(c->ev_block[i]);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
         cudaFree(c->dev_status);
         cudaFreeHost(c->host_mailbox);
@@ -289,6 +306,8 @@ int b2_destroy(b2_handle h) {
     }
     cudaStreamDestroy(c->copy_stream);
     cudaFreeHost(c->result_ring);
+    cudaFreeHost(c->count_ring);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_block[i]);
     delete[] c->ring_first;
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -322,8 +341,14 @@ int b2_synchronize(b2_handle h) {
 
 int b2_set_icp_driver(b2_handle h, int driver) {
     CTX(h);
-    if (driver < B2_ICP_DRIVER_AUTO || driver > B2_ICP_DRIVER_SWEEP4)
-        return set_error(c, B2_ERR_INVALID, "b2_set_icp_driver: unknown driver %d", driver);
+#ifdef B2_EXPERIMENTS
+    const int last = B2_ICP_DRIVER_SWEEP4;
+#else
+    const int last = B2_ICP_DRIVER_SWEEP;
+#endif
+    if (driver < B2_ICP_DRIVER_AUTO || driver > last)
+        return set_error(c, B2_ERR_INVALID, "b2_set_icp_driver: unknown driver %d%s", driver,
+                         driver == B2_ICP_DRIVER_SWEEP4 ? " (SWEEP4 is an experiment: build with B2_EXPERIMENTS=1)" : "");
     c->icp_driver = driver;
     return B2_OK;
 }
@@ -646,7 +671,23 @@ int b2_map_size(b2_handle h, long long* n_voxels) {
 int b2_map_export(b2_handle h, float* out_pts_dev, int* out_keys_dev, long long max_out, long long* n_out) {
     CTX(h);
     if (!out_pts_dev || max_out < 0) return set_error(c, B2_ERR_INVALID, "b2_map_export: bad arguments");
-    return map_export(c, (float4*)out_pts_dev, out_keys_dev, max_out, n_out);
+    return map_export(c, (float4*)out_pts_dev, out_keys_dev, nullptr, max_out, n_out);
+}
+
+int b2_map_export_records(b2_handle h, int* out_keys_dev, double* out_sums_dev, long long max_out, long long* n_out) {
+    CTX(h);
+    if (!out_keys_dev || !out_sums_dev || max_out < 0)
+        return set_error(c, B2_ERR_INVALID, "b2_map_export_records: bad arguments");
+    return map_export(c, nullptr, out_keys_dev, out_sums_dev, max_out, n_out);
+}
+
+int b2_map_merge_records(b2_handle h, const int* keys_dev, const double* sums_dev, long long n) {
+    CTX(h);
+    if (n < 0 || n > 0x7fffffffLL || (n > 0 && (!keys_dev || !sums_dev)))
+        return set_error(c, B2_ERR_INVALID, "b2_map_merge_records: bad arguments");
+    if (n == 0) return B2_OK;
+    B2_TRY(map_merge_records(c, keys_dev, sums_dev, (int)n));
+    return check_status(c);
 }
 
 int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
@@ -716,6 +757,12 @@ int b2_slam_get_pose(b2_handle h, double* T) {
     return B2_OK;
 }
 
+// After a failed step the host's view of the map ("has anything been fused yet?") is re-read from the device.
+static void slam_resync_after_failure(Context* c) {
+    long long voxels = 0;
+    if (map_counts(c, nullptr, &voxels) == B2_OK) map_set_voxels_bound(c, voxels);
+}
+
 // Everything of one scan step after the scan sits in the fixed device buffer `scan`:
 // down-sample -> ICP against the resident map (pose chained on the device) -> fuse.
 static int slam_body(Context* c, const float4* scan, int n, const int* n_dev, double ds_voxel,
@@ -741,8 +788,11 @@ static int slam_body(Context* c, const float4* scan, int n, const int* n_dev, do
         B2_TRY(map_grid_view(c, &g));
         B2_TRY(icp_run(c, src, n, nullptr, ns_dev, 1, g, nullptr, nullptr, pose, to_internal(params), res, nullptr,
                        nullptr, 0, 0));
-        copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose);
+        // fuse with the registered pose straight from the result record; the pose prior is committed last
+        B2_TRY(map_fuse(c, scan, n, n_dev, res->T));
+        copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose, c->dev_status);
         B2_LAUNCH_CHECK(c);
+        return B2_OK;
     }
     B2_TRY(map_fuse(c, scan, n, n_dev, pose));
     return B2_OK;
@@ -756,7 +806,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
                              const b2_icp_params* params) {
     static const bool no_graph = getenv("B2_NO_GRAPH") != nullptr;
     ScanGraph& sg = c->scan_graph;
-    const bool same = sg.n == n && sg.ds_voxel == ds_voxel && sg.scan == scan &&
+    const bool same = sg.n == n && sg.ds_voxel == ds_voxel && sg.scan == scan && sg.passes_hint == c->sort_passes_hint &&
                       std::memcmp(&sg.params, params, sizeof(*params)) == 0 && sg.generation == c->ws_generation;
     if (no_graph) return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
     if (same && sg.exec) {
@@ -769,6 +819,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
         sg.exec = nullptr;
         B2_TRY(slam_body(c, scan, n, n_dev, ds_voxel, params, false));
         sg.n = n; sg.ds_voxel = ds_voxel; sg.scan = scan; sg.params = *params; sg.generation = c->ws_generation;
+        sg.passes_hint = c->sort_passes_hint;
         return B2_OK;
     }
     // second call with this key: capture
@@ -809,9 +860,24 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
     const int cap = (n + 8191) / 8192 * 8192;
     B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)cap);
     B2_WS(c, n_dev, int, WS_SCAN_COUNT, sizeof(int) * 4);
-    int* hn = (int*)c->host_mailbox + 760 + (c->scan_seq++ & 7);  // small ring: the copy is asynchronous
-    *hn = n;
-    B2_CUDA_OK(c, cudaMemcpyAsync(n_dev, hn, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    {   // the live count goes through a pinned ring slot of its own: the copy below is asynchronous and a caller
+        // that passes out == NULL runs many scans ahead of the device
+        const unsigned slot = c->scan_seq % kResultRing;
+        constexpr unsigned kPerBlock = kResultRing / 4;
+        if (slot % kPerBlock == 0) {
+            const int blk = (int)(slot / kPerBlock);
+            // entering block blk: its previous use (kResultRing scans ago) must have run.  Everything up to the
+            // start of the block after it was covered by that block's event.
+            const int guard = (blk + 1) & 3;
+            if (c->block_valid[guard]) B2_CUDA_OK(c, cudaEventSynchronize(c->ev_block[guard]));
+            B2_CUDA_OK(c, cudaEventRecord(c->ev_block[blk], c->stream));
+            c->block_valid[blk] = true;
+        }
+        c->scan_seq++;
+        int* hn = c->count_ring + slot;
+        *hn = n;
+        B2_CUDA_OK(c, cudaMemcpyAsync(n_dev, hn, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    }
     if (scan_dev) {
         B2_CUDA_OK(c, cudaMemcpyAsync(scan, scan_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
     } else {
@@ -850,7 +916,29 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
         } else {
             B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
         }
-        B2_TRY(check_status(c));
+        int rc = check_status(c);
+        if (rc == B2_ERR_KEY_RANGE && c->sort_passes_hint < 8) {
+            // the scan's voxel extent needs more radix passes than the captured step launches: nothing was
+            // committed (pose and map are gated on the status word), so run the step again with the full
+            // budget; the graph is keyed on the budget and is re-captured for the following scans
+            c->sort_passes_hint = 8;
+            IcpResultDev* rr = (IcpResultDev*)c->result_ring + (int)((c->scans_total - 1) % kResultRing);
+            if (map_empty) {
+                map_set_voxels_bound(c, 0);
+                B2_TRY(slam_body(c, scan, cap, n_dev, ds_voxel, params, true));
+                B2_CUDA_OK(c, cudaMemcpyAsync(hr->T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
+                B2_CUDA_OK(c, cudaMemcpyAsync(rr->T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
+            } else {
+                B2_TRY(slam_body_graphed(c, scan, cap, n_dev, ds_voxel, params));
+                B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+                B2_CUDA_OK(c, cudaMemcpyAsync(rr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+            }
+            rc = check_status(c);
+        }
+        if (rc != B2_OK) {
+            slam_resync_after_failure(c);
+            return rc;
+        }
         fill_result(hr, out);
     }
     return B2_OK;
@@ -883,7 +971,17 @@ int b2_slam_results(b2_handle h, int count, b2_icp_result* out) {
     if ((unsigned long long)count > c->scans_total || count > kResultRing)
         return set_error(c, B2_ERR_INVALID, "b2_slam_results: %d results asked, %llu scans registered, ring of %d",
                          count, c->scans_total, kResultRing);
-    B2_TRY(check_status(c));  // waits for the stream: every pending result has landed in the ring
+    {   // waits for the stream: every pending result has landed in the ring
+        const int rc = check_status(c);
+        if (rc != B2_OK) {
+            // a deferred scan failed on the device: from that scan on nothing was committed (pose and map are
+            // gated on the status word).  Widen the sort budget so that resubmitting the scans succeeds.
+            if (rc == B2_ERR_KEY_RANGE) c->sort_passes_hint = 8;
+            slam_resync_after_failure(c);
+            c->last_error += "; scans submitted since the failing one were not applied, resubmit them";
+            return rc;
+        }
+    }
     for (int i = 0; i < count; ++i) {
         const int slot = (int)((c->scans_total - (unsigned long long)count + i) % kResultRing);
         IcpResultDev r = ((const IcpResultDev*)c->result_ring)[slot];

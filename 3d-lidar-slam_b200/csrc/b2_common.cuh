@@ -56,6 +56,7 @@ struct ScanGraph {
     b2_icp_params params{};
     unsigned long long generation = 0;
     int kernel_nodes = 0;
+    int passes_hint = 0;  // radix pass budget baked into the captured sorts
 };
 
 struct Context {
@@ -83,6 +84,12 @@ struct Context {
     void* result_ring = nullptr;
     unsigned char* ring_first = nullptr;   // slot holds a first-scan record (pose only)
     unsigned long long scans_total = 0;
+    // live point count of every submitted scan: pinned ring as deep as the result ring (the H2D copy of a
+    // count is asynchronous, so a slot must stay untouched until the scan that uses it has run).  The ring is
+    // split in four blocks with one event each; the host waits for a block's previous use before reusing it.
+    int* count_ring = nullptr;
+    cudaEvent_t ev_block[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool block_valid[4] = {false, false, false, false};
 };
 constexpr int kResultRing = 1024;
 
@@ -431,11 +438,13 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
 int map_grid_view(Context* c, GridView* g);
 int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev);
 int map_counts(Context* c, long long* cells, long long* voxels);
-int map_export(Context* c, float4* out_pts, int* out_keys, long long max_out, long long* n_out);
+int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, long long max_out, long long* n_out);
+int map_merge_records(Context* c, const int* keys3, const double* sums, int n);
 double* map_pose_dev(Context* c);
 IcpResultDev* map_result_dev(Context* c);
 double map_voxel(Context* c);
 double map_max_corr(Context* c);
 bool map_is_empty_host(Context* c);
+void map_set_voxels_bound(Context* c, long long voxels);
 
 }  // namespace b2

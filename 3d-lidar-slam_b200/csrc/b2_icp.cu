@@ -18,7 +18,7 @@
 //   b2_icp_solve.cuh    the per-step solve
 //   b2_icp_group.cuh    icp_iter_kernel: four lanes per query, probes in parallel (dense map, single pairs)
 //   b2_icp_sweep.cuh    icp_sweep_kernel: one thread per query, pruned walk (batches on pair / slab grids)
-//   b2_icp_persist.cuh  opt-in persistent driver (experiment)
+//   b2_icp_persist.cuh  persistent driver — experiment, only built with -DB2_EXPERIMENTS (B2_EXPERIMENTS=1 build)
 //   this file           launchers, the driver choice, the chained-launch / WHILE-node loop (icp_run)
 //
 // Algorithmic bytes of one launch: 16*Ns (queries) + 16*sum_q cand(q) (candidate points) +
@@ -40,7 +40,9 @@ constexpr unsigned kFull = 0xffffffffu;
 #include "b2_icp_solve.cuh"
 #include "b2_icp_group.cuh"
 #include "b2_icp_sweep.cuh"
-#include "b2_icp_persist.cuh"
+#ifdef B2_EXPERIMENTS
+#include "b2_icp_persist.cuh"  // opt-in persistent driver (measured slower inside the captured scan step)
+#endif
 
 __global__ void icp_init_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs,
                                 const int* __restrict__ ns_dev, int ns_max, const double* __restrict__ init,
@@ -169,6 +171,7 @@ int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev
     return B2_OK;
 }
 
+#ifdef B2_EXPERIMENTS
 namespace {
 
 template <int MODE, int KIND>
@@ -203,18 +206,27 @@ int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max,
 }
 
 }  // namespace
+#endif  // B2_EXPERIMENTS
 
 // The sweep kernels keep one accumulator column per thread in dynamic shared memory (> 48 KB): opt in once
 // per context (device attribute, not a stream operation — done at creation so it never lands in a capture).
 int icp_configure(Context* c) {
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+#ifdef B2_EXPERIMENTS
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+#endif
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+#ifdef B2_EXPERIMENTS
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<0>::kSmem));
+#endif
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+#ifdef B2_EXPERIMENTS
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+#endif
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+#ifdef B2_EXPERIMENTS
     B2_CUDA_OK(c, cudaFuncSetAttribute(icp_sweep_kernel<1, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepCfg<1>::kSmem));
+#endif
     return B2_OK;
 }
 
@@ -271,6 +283,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     B2_LAUNCH_CHECK(c);
     dim3 g(gx, n_pairs);
     const int launches = search_only ? 1 : prm.max_iter + 1;
+#ifdef B2_EXPERIMENTS
     // (opt-in: on B200 the software grid barrier + solve of a step costs more than a kernel boundary)
     static const bool persist = getenv("B2_PERSIST") != nullptr;
     if (persist && n_pairs == 1 && !src_offsets && !search_only && !d2_out && !c->capturing) {
@@ -302,6 +315,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
 #endif
         return rc;
     }
+#endif  // B2_EXPERIMENTS
     int* host_done = (int*)c->host_mailbox + 512;  // scratch word in the pinned mailbox
     // B2_TIMING=1: bracket every launch with CUDA events and print the per-launch device times
     static const bool timing_env = getenv("B2_TIMING") != nullptr;
@@ -326,12 +340,18 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
 #define B2_ICP_LAUNCH(M, K)                                                                                   \
     launch_iter<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
                       tickets, results_dev, corr_out, ndone, d2_out, search_only, launch_stream, loop_handle)
-#define B2_ICP_SWEEP(M, K)                                                                                     \
-    do {                                                                                                       \
+#ifdef B2_EXPERIMENTS
+#define B2_SWEEP4_BRANCH(M, K)                                                                                 \
         if (sweep_lanes == 4)                                                                                  \
             launch_sweep<M, K, 4>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, \
                                   partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);       \
-        else                                                                                                   \
+        else
+#else
+#define B2_SWEEP4_BRANCH(M, K)
+#endif
+#define B2_ICP_SWEEP(M, K)                                                                                     \
+    do {                                                                                                       \
+        B2_SWEEP4_BRANCH(M, K)                                                                                 \
             launch_sweep<M, K, 1>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, \
                                   partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);       \
     } while (0)
@@ -350,6 +370,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         }
 #undef B2_ICP_LAUNCH
 #undef B2_ICP_SWEEP
+#undef B2_SWEEP4_BRANCH
     };
     for (int it = 0; it < chained; ++it) {
         launch_one(c->stream, 0ull);

@@ -79,7 +79,7 @@ map_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums,
                  unsigned long long max_cells, int* __restrict__ dev_status) {
     pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
-    if (j >= ctl->nseg) return;
+    if (j >= ctl->nseg || *dev_status != 0) return;  // a step that already failed must not touch the map
     const int kx = keys3[3 * j], ky = keys3[3 * j + 1], kz = keys3[3 * j + 2];
     const int cx = floor_div(kx, brick), cy = floor_div(ky, brick), cz = floor_div(kz, brick);
     const int lim = (1 << 20) - 2;
@@ -166,7 +166,7 @@ vox_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums,
                  long long* __restrict__ counters, unsigned long long max_cells, int* __restrict__ dev_status) {
     pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
-    if (j >= ctl->nseg) return;
+    if (j >= ctl->nseg || *dev_status != 0) return;  // a step that already failed must not touch the map
     const int kx = keys3[3 * j], ky = keys3[3 * j + 1], kz = keys3[3 * j + 2];
     const int lim = (1 << 20) - 2;
     if (kx < -lim || kx > lim || ky < -lim || ky > lim || kz < -lim || kz > lim) {
@@ -228,13 +228,17 @@ __global__ void __launch_bounds__(kBlock)
 vox_export_write_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
                         const unsigned* __restrict__ valsA, const unsigned* __restrict__ valsB,
                         const SortCtl* __restrict__ ctl, const VoxEntry* __restrict__ vox,
-                        float4* __restrict__ out_pts, int* __restrict__ out_keys) {
+                        const double* __restrict__ acc, float4* __restrict__ out_pts, int* __restrict__ out_keys,
+                        double* __restrict__ out_sums) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= ctl->n) return;
     const bool odd = ctl->npasses & 1;
     const unsigned long long k = (odd ? keysB : keysA)[i];
-    const VoxEntry e = vox[(odd ? valsB : valsA)[i]];
-    out_pts[i] = make_float4(e.x, e.y, e.z, __int_as_float((int)e.n));
+    const unsigned pos = (odd ? valsB : valsA)[i];
+    const VoxEntry e = vox[pos];
+    if (out_pts) out_pts[i] = make_float4(e.x, e.y, e.z, __int_as_float((int)e.n));
+    if (out_sums)
+        for (int d = 0; d < 4; ++d) out_sums[4 * (size_t)i + d] = acc[4 * (size_t)pos + d];
     if (out_keys) {
         out_keys[3 * i] = (int)((k >> 42) & 0x1FFFFF) - (1 << 20);
         out_keys[3 * i + 1] = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
@@ -280,15 +284,20 @@ __global__ void __launch_bounds__(kBlock)
 map_export_write_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
                         const unsigned* __restrict__ valsA, const unsigned* __restrict__ valsB,
                         const SortCtl* __restrict__ ctl, const float4* __restrict__ cent,
-                        const double* __restrict__ acc, float4* __restrict__ out_pts, int* __restrict__ out_keys) {
+                        const double* __restrict__ acc, float4* __restrict__ out_pts, int* __restrict__ out_keys,
+                        double* __restrict__ out_sums) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i >= ctl->n) return;
     const bool odd = ctl->npasses & 1;
     const unsigned long long k = (odd ? keysB : keysA)[i];
     const unsigned pos = (odd ? valsB : valsA)[i];
-    float4 p = cent[pos];
-    p.w = __int_as_float((int)acc[4 * (size_t)pos + 3]);
-    out_pts[i] = p;
+    if (out_pts) {
+        float4 p = cent[pos];
+        p.w = __int_as_float((int)acc[4 * (size_t)pos + 3]);
+        out_pts[i] = p;
+    }
+    if (out_sums)
+        for (int d = 0; d < 4; ++d) out_sums[4 * (size_t)i + d] = acc[4 * (size_t)pos + d];
     if (out_keys) {
         out_keys[3 * i] = (int)((k >> 42) & 0x1FFFFF) - (1 << 20);
         out_keys[3 * i + 1] = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
@@ -340,33 +349,48 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
     int brick = (int)ceil(max_corr / voxel - 1e-9);
     if (brick < 1) brick = 1;
     if (brick > 6) return set_error(c, B2_ERR_INVALID, "map_init: max_corr/voxel = %g > 6 is not supported", max_corr / voxel);
-    map_free(c);
-    c->ws_generation++;  // invalidates any captured graph that baked the old table addresses
     unsigned long long cap = 1024;
     while (cap < (unsigned long long)capacity_cells) cap <<= 1;
     const int cap_slots = brick * brick * brick;
     if (cap * (unsigned long long)cap_slots >= 0xFFFFFFFFull)
         return set_error(c, B2_ERR_INVALID, "map_init: capacity %llu cells x %d slots exceeds 2^32", cap, cap_slots);
+    // the old map goes first (its tables may be most of the memory the new one needs); the new one is only
+    // published once every table exists and has been cleared, so a failed allocation leaves NO map (every
+    // map call then reports B2_ERR_STATE) instead of a half-initialised one
+    map_free(c);
+    c->ws_generation++;  // invalidates any captured graph that baked the old table addresses
     MapState* m = new MapState();
-    c->map = m;
     m->voxel = voxel; m->max_corr = max_corr; m->brick = brick; m->cap_slots = cap_slots;
     m->lut_stride = (cap_slots + 15) / 16 * 16;
     m->capacity = (unsigned)cap;
     for (int d = 0; d < 3; ++d) m->origin[d] = origin[d];
-    if (brick == 1) {
-        B2_CUDA_OK(c, cudaMalloc(&m->vox, sizeof(VoxEntry) * cap));
-    } else {
-        B2_CUDA_OK(c, cudaMalloc(&m->entries, sizeof(CellEntry) * cap));
-        B2_CUDA_OK(c, cudaMalloc(&m->lut, (size_t)cap * m->lut_stride));
-        B2_CUDA_OK(c, cudaMalloc(&m->lid, (size_t)cap * cap_slots));
-        B2_CUDA_OK(c, cudaMalloc(&m->cent, sizeof(float4) * cap * cap_slots));
+    auto alloc_all = [&]() -> cudaError_t {
+        cudaError_t e;
+        if (brick == 1) {
+            if ((e = cudaMalloc(&m->vox, sizeof(VoxEntry) * cap)) != cudaSuccess) return e;
+        } else {
+            if ((e = cudaMalloc(&m->entries, sizeof(CellEntry) * cap)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->lut, (size_t)cap * m->lut_stride)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->lid, (size_t)cap * cap_slots)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->cent, sizeof(float4) * cap * cap_slots)) != cudaSuccess) return e;
+        }
+        if ((e = cudaMalloc(&m->acc, sizeof(double) * 4 * cap * cap_slots)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&m->counters, sizeof(long long) * 2)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&m->meta, sizeof(GridMeta))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&m->pose, sizeof(double) * 16)) != cudaSuccess) return e;
+        return cudaMalloc(&m->result, sizeof(IcpResultDev));
+    };
+    const cudaError_t e = alloc_all();
+    c->map = m;  // (map_free / map_reset work on c->map)
+    if (e != cudaSuccess) {
+        map_free(c);
+        cudaGetLastError();
+        return set_error(c, B2_ERR_CUDA, "map_init: allocating the tables of %llu cells failed: %s", cap,
+                         cudaGetErrorString(e));
     }
-    B2_CUDA_OK(c, cudaMalloc(&m->acc, sizeof(double) * 4 * cap * cap_slots));
-    B2_CUDA_OK(c, cudaMalloc(&m->counters, sizeof(long long) * 2));
-    B2_CUDA_OK(c, cudaMalloc(&m->meta, sizeof(GridMeta)));
-    B2_CUDA_OK(c, cudaMalloc(&m->pose, sizeof(double) * 16));
-    B2_CUDA_OK(c, cudaMalloc(&m->result, sizeof(IcpResultDev)));
-    return map_reset(c);
+    const int rc = map_reset(c);
+    if (rc != B2_OK) map_free(c);
+    return rc;
 }
 
 int map_grid_view(Context* c, GridView* g) {
@@ -385,6 +409,7 @@ double* map_pose_dev(Context* c) { return c->map ? c->map->pose : nullptr; }
 IcpResultDev* map_result_dev(Context* c) { return c->map ? c->map->result : nullptr; }
 double map_voxel(Context* c) { return c->map ? c->map->voxel : 0.0; }
 bool map_is_empty_host(Context* c) { return !c->map || c->map->host_voxels_bound == 0; }
+void map_set_voxels_bound(Context* c, long long voxels) { if (c->map) c->map->host_voxels_bound = voxels; }
 double map_max_corr(Context* c) { return c->map ? c->map->max_corr : 0.0; }
 
 // Fuse n_max (or *n_dev) points, transformed by T_dev (device, may be null), into the map.
@@ -412,6 +437,36 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
     return B2_OK;
 }
 
+namespace {
+__global__ void set_nseg_kernel(SortCtl* ctl, int n) {
+    ctl->n = n;
+    ctl->nseg = n;
+    ctl->status = 0;
+}
+}  // namespace
+
+// Merge n exported voxel records (unique keys; (sum x, sum y, sum z, count) per voxel) into the map:
+// acc += record, centroid refreshed — the K10 centroid merge weighted by the record's count.
+int map_merge_records(Context* c, const int* keys3, const double* sums, int n) {
+    MapState* m = c->map;
+    if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
+    if (n <= 0) return B2_OK;
+    B2_WS(c, ctl, SortCtl, WS_CTL, sizeof(SortCtl));
+    set_nseg_kernel<<<1, 1, 0, c->stream>>>(ctl, n);
+    B2_LAUNCH_CHECK(c);
+    const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
+    if (m->brick == 1)
+        pdl_launch(vox_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums,
+                   (const SortCtl*)ctl, m->vox, m->capacity - 1, m->acc, m->counters, max_cells, c->dev_status);
+    else
+        pdl_launch(map_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums,
+                   (const SortCtl*)ctl, m->entries, m->capacity - 1, m->lut, m->lid, m->cent, m->acc, m->counters,
+                   m->brick, m->cap_slots, m->lut_stride, max_cells, c->dev_status);
+    B2_LAUNCH_CHECK(c);
+    m->host_voxels_bound += n;
+    return B2_OK;
+}
+
 int map_counts(Context* c, long long* cells, long long* voxels) {
     MapState* m = c->map;
     if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
@@ -423,7 +478,7 @@ int map_counts(Context* c, long long* cells, long long* voxels) {
     return B2_OK;
 }
 
-int map_export(Context* c, float4* out_pts, int* out_keys, long long max_out, long long* n_out) {
+int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, long long max_out, long long* n_out) {
     MapState* m = c->map;
     if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
     long long voxels = 0;
@@ -453,10 +508,10 @@ int map_export(Context* c, float4* out_pts, int* out_keys, long long max_out, lo
     B2_LAUNCH_CHECK(c);
     if (m->brick == 1)
         vox_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->vox,
-                                                                            out_pts, out_keys);
+                                                                            m->acc, out_pts, out_keys, out_sums);
     else
         map_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->cent,
-                                                                            m->acc, out_pts, out_keys);
+                                                                            m->acc, out_pts, out_keys, out_sums);
     B2_LAUNCH_CHECK(c);
     B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return B2_OK;

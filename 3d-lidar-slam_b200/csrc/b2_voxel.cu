@@ -368,8 +368,10 @@ int voxel_sort(Context* c, const float4* pts, int n_max, const int* n_dev, const
                double voxel, int origin_mode, const double* origin_host, const double* T_dev, int* cloud_out_offs,
                VoxelSortOut* out) {
     if (n_max <= 0 || n_clouds <= 0) return set_error(c, B2_ERR_INVALID, "voxel_sort: empty input");
+#ifdef B2_EXPERIMENTS
     if (!cloud_offsets && !cloud_out_offs && voxel_small_applicable(n_max, n_clouds))
         return voxel_small(c, pts, n_max, n_dev, voxel, origin_mode, origin_host, T_dev, false, DownsampleOut{}, out);
+#endif
     if (!(voxel > 0.0)) return set_error(c, B2_ERR_INVALID, "voxel size must be > 0 (got %g)", voxel);
     B2_WS(c, keysA, unsigned long long, WS_KEYS_A, sizeof(unsigned long long) * (size_t)n_max);
     B2_WS(c, keysB, unsigned long long, WS_KEYS_B, sizeof(unsigned long long) * (size_t)n_max);
@@ -413,8 +415,10 @@ int voxel_sort(Context* c, const float4* pts, int n_max, const int* n_dev, const
 int voxel_downsample(Context* c, const float4* pts, int n_max, const int* n_dev, const int* cloud_offsets_in,
                      int n_clouds, double voxel, int origin_mode, const double* origin_host, const double* T_dev,
                      DownsampleOut out, VoxelSortOut* vs_out) {
+#ifdef B2_EXPERIMENTS
     if (!cloud_offsets_in && !out.cloud_offsets && voxel_small_applicable(n_max, n_clouds))
         return voxel_small(c, pts, n_max, n_dev, voxel, origin_mode, origin_host, T_dev, true, out, vs_out);
+#endif
     VoxelSortOut vs;
     B2_TRY(voxel_sort(c, pts, n_max, n_dev, cloud_offsets_in, n_clouds, voxel, origin_mode, origin_host, T_dev,
                       out.cloud_offsets, &vs));

@@ -29,10 +29,17 @@ import queue as _queue  # noqa: E402
 import time as _time  # noqa: E402
 
 
-def drain_pending(q, max_items: int, first_timeout: float = 0.1):
-    """Batch dequeue: wait up to ``first_timeout`` for one scan, then take whatever else is already queued
-    (at most ``max_items``) without blocking.  Replaces the reference's ``empty()`` poll + ``sleep(0.1)``
-    (process_pc_manager.py:49-51), which adds up to 100 ms of latency per scan and dequeues one at a time."""
+def drain_pending(q, max_items: int, first_timeout: float = 0.1, linger: float = 0.005):
+    """Batch dequeue: wait up to ``first_timeout`` for one scan, then keep taking scans (at most ``max_items``)
+    for as long as the next one shows up within ``linger`` seconds.  Replaces the reference's ``empty()`` poll +
+    ``sleep(0.1)`` (process_pc_manager.py:49-51), which adds up to 100 ms of latency per scan and dequeues one
+    at a time.
+
+    Why a linger and not ``get_nowait()``: a ``multiprocessing.Queue`` (data_transfer.py:13) hands items over
+    through a feeder thread and a 64 KB pipe, so a 590 KB scan record that was ``put`` long ago is still not
+    "already there" the instant the previous record has been read — ``get_nowait()`` raises ``Empty`` on a
+    backlog and the batch never forms.  A short blocking ``get`` lets the feeder push the next record; the
+    cost is at most ``linger`` of added latency at the end of a batch."""
     items = []
     try:
         items.append(q.get(timeout=first_timeout))
@@ -41,6 +48,13 @@ def drain_pending(q, max_items: int, first_timeout: float = 0.1):
     while len(items) < max_items:
         try:
             items.append(q.get_nowait())
+            continue
+        except _queue.Empty:
+            pass
+        if linger <= 0.0:
+            break
+        try:
+            items.append(q.get(timeout=linger))
         except _queue.Empty:
             break
     return items
@@ -74,13 +88,14 @@ class ProcessLoop:
     ``reset`` / ``global_map``."""
 
     def __init__(self, processor, data_transfer, stop_event, reset_event, max_batch: int = 64,
-                 idle_timeout: float = 0.1, logger=None):
+                 idle_timeout: float = 0.1, logger=None, linger: float = 0.005):
         self.processor = processor
         self.data_transfer = data_transfer
         self.stop_event = stop_event
         self.reset_event = reset_event
         self.max_batch = int(max_batch)
         self.idle_timeout = float(idle_timeout)
+        self.linger = float(linger)
         self.logger = logger
         self.scans_processed = 0
         self.batches = 0
@@ -94,7 +109,7 @@ class ProcessLoop:
             self.processor.reset()
             _time.sleep(0.001)  # the reference spins here until the event is cleared (process_pc_manager.py:44-47)
             return 0
-        scans = drain_pending(self.data_transfer.pixel_depth_map_queue, self.max_batch, self.idle_timeout)
+        scans = drain_pending(self.data_transfer.pixel_depth_map_queue, self.max_batch, self.idle_timeout, self.linger)
         if not scans:
             return 0
         take = getattr(self.processor, "process_records", None)

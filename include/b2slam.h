@@ -74,7 +74,7 @@ unsigned long long b2_launch_count(b2_handle h);
 #define B2_ICP_DRIVER_AUTO 0
 #define B2_ICP_DRIVER_GROUP 1
 #define B2_ICP_DRIVER_SWEEP 2
-#define B2_ICP_DRIVER_SWEEP4 3 /* the sweep kernel with four lanes per query (small problems) */
+#define B2_ICP_DRIVER_SWEEP4 3 /* experiment (measured slower), only in B2_EXPERIMENTS=1 builds: four lanes per query */
 int b2_set_icp_driver(b2_handle h, int driver);
 
 /* ---- layout helpers ----------------------------------------------------- */
@@ -161,6 +161,13 @@ int b2_map_size(b2_handle h, long long* n_voxels);
 /* Voxel centroids in canonical key order: out_pts_dev float32 [max_out,4] (w = count bits),
  * out_keys_dev int32 [max_out,3] or NULL. */
 int b2_map_export(b2_handle h, float* out_pts_dev, int* out_keys_dev, long long max_out, long long* n_out);
+/* The map as mergeable records, canonical key order: out_keys_dev int32 [max_out,3] voxel keys and
+ * out_sums_dev float64 [max_out,4] = (sum x, sum y, sum z, point count) of every voxel — what ranks exchange
+ * when partial maps are gathered.  b2_map_merge_records adds such records (unique
+ * keys within one call) to the resident map: per voxel the sums and counts add up, so merging the records of
+ * several partial maps equals voxel_down_sample of the concatenated points (icp_processor.py:74,132-133). */
+int b2_map_export_records(b2_handle h, int* out_keys_dev, double* out_sums_dev, long long max_out, long long* n_out);
+int b2_map_merge_records(b2_handle h, const int* keys_dev, const double* sums_dev, long long n);
 /* registration_icp with the resident map as the target (icp_processor.py:68-69,103-113). */
 int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
                b2_icp_result* out);
@@ -191,7 +198,10 @@ int b2_stencil_candidates(b2_handle h, const float* src_dev, int ns, const float
 int b2_slam_set_pose(b2_handle h, const double* T);
 int b2_slam_get_pose(b2_handle h, double* T);
 
-/* ---- batched independent pairs (loop-closure candidates / offline replay) ---- */
+/* ---- batched independent pairs (loop-closure candidates / offline replay) ----
+ * The batch calls are ASYNCHRONOUS: they enqueue the whole batch on the handle's stream and return; the
+ * records in results_dev are complete, and device-side failures (B2_ERR_KEY_RANGE from a grid or voxel sort,
+ * ...) are reported, by the next b2_synchronize(h) — call it before reading results_dev from another stream. */
 /* src_dev/tgt_dev: concatenated float32 [sum,4]; *_offsets_dev: int32 [n_pairs+1] (device).
  * ds_voxel > 0: both clouds of every pair are voxel-down-sampled first (icp_processor.py:90-91).
  * init_dev: float64 [n_pairs,16] device or NULL (identity).  results_dev: device array of

@@ -1,5 +1,6 @@
-"""BASELINE.json-sized checks through size-independent properties (the oracle would need minutes
-at these sizes): 2 M-voxel resident map, 49k-pt scans."""
+"""BASELINE.json-sized checks: 2 M-voxel resident map, 49k-pt scans.  The map itself is checked through
+size-independent properties; the registration the bench times (dense-map ICP step kernel against the full
+2 M-voxel table) is checked against the oracle run on the exported centroids."""
 import numpy as np
 import pytest
 import torch
@@ -60,6 +61,57 @@ def test_full_size_scan_to_map_registration(engine, b2, big_map):
     engine.map_fuse(engine.pack(scan), res.matrix())
     after = engine.map_size()
     assert before <= after < before + 3000  # a registered scan lands almost entirely in existing voxels
+
+
+def test_full_size_config2_registration_matches_the_oracle(engine, b2, big_map):
+    """BASELINE config 2 at full size (icp_processor.py:103-113): three consecutive 49k-pt scans, each 2 cm
+    down-sampled and registered against the 2 M-voxel map by the dense-map step kernel, versus
+    ``registration_icp`` of the oracle on the map's exported centroids.  Iterations, correspondence count and
+    fitness equal; transform within 1e-4 rad / 1e-4 m."""
+    from lidar_slam_b200 import synth
+    from oracle import cpu as orc
+
+    scene, _ = big_map
+    cent, _ = engine.map_export(want_keys=False)
+    tgt = cent.cpu().numpy()[:, :3].astype(np.float64)
+    assert len(tgt) > 1_500_000
+    poses = synth.corridor_trajectory(scene, 3, start_x=60.0, step=0.02, seed=5)
+    prm = b2.make_params(0.05, 30)
+    for k, pose in enumerate(poses):
+        scan = synth.render_scan(scene, pose, seed=700 + k).numpy()
+        sd, _ = engine.voxel_downsample(engine.pack(scan), 0.02, want_keys=False)
+        init = synth.perturb_pose(pose, 40 + k, trans=0.015, rot_deg=0.4)
+        res = engine.map_icp(sd, prm, init=init)
+        src = sd.cpu().numpy()[:, :3].astype(np.float64)
+        ores = orc.registration_icp(src, tgt, 0.05, init=init, max_iteration=30)
+        assert res.iterations == ores.iterations, k
+        assert res.n_correspondences == int((ores.correspondence >= 0).sum()), k
+        assert res.fitness == ores.fitness, k
+        assert res.inlier_rmse == pytest.approx(ores.inlier_rmse, rel=1e-9, abs=1e-12)
+        assert_transform_close(res.matrix(), ores.transformation)
+        assert res.fitness > 0.8  # a real registration, not an empty overlap
+
+
+def test_full_size_pair_through_the_sweep_driver_matches_the_oracle(engine, b2):
+    """One full-size config-1 pair (49k-pt scans, 2 cm down-sampled) forced through the thread-per-query sweep
+    kernel versus the oracle (round 1 compared the sweep driver with the group kernel only at this size)."""
+    from lidar_slam_b200 import synth
+    from oracle import cpu as orc
+
+    src, tgt, _ = synth.make_pair(31)
+    sd, _ = engine.voxel_downsample(engine.pack(src.numpy()), 0.02, want_keys=False)
+    td, _ = engine.voxel_downsample(engine.pack(tgt.numpy()), 0.02, want_keys=False)
+    engine.set_icp_driver("sweep")
+    try:
+        res, corr = engine.icp(sd, td, b2.make_params(0.05, 30), want_corr=True)
+    finally:
+        engine.set_icp_driver("auto")
+    ores = orc.registration_icp(sd.cpu().numpy()[:, :3].astype(np.float64), td.cpu().numpy()[:, :3].astype(np.float64),
+                                0.05, max_iteration=30)
+    assert res.iterations == ores.iterations
+    assert res.fitness == ores.fitness
+    np.testing.assert_array_equal(corr.cpu().numpy(), ores.correspondence)
+    assert_transform_close(res.matrix(), ores.transformation)
 
 
 def test_large_batch_takes_the_sweep_driver_and_agrees_with_single_pair_runs(engine, b2):

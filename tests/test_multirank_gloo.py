@@ -43,3 +43,42 @@ def test_two_rank_gather_reassembles_every_pair(tmp_path):
     np.testing.assert_array_equal(rec["iterations"], np.arange(n_pairs))
     for pair in range(n_pairs):
         np.testing.assert_array_equal(rec["transformation"][pair], np.eye(4) * (pair + 1))
+
+
+def _map_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import lidar_slam_b200  # noqa: F401
+    from lidar_slam_b200.batch import ResultGatherer, gather_map_records
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    # rank r holds a partial map of 3 + 2r voxels (ragged), records keyed by (rank, i)
+    n = 3 + 2 * rank
+    keys = torch.tensor([[rank, i, -i] for i in range(n)], dtype=torch.int32)
+    sums = torch.tensor([[rank + 0.5, i, 2.0 * i, i + 1] for i in range(n)], dtype=torch.float64)
+    parts = gather_map_records(keys, sums)
+    np.savez(os.path.join(out_dir, f"map{rank}.npz"), **{f"k{r}": k.numpy() for r, (k, _) in enumerate(parts)},
+             **{f"s{r}": s.numpy() for r, (_, s) in enumerate(parts)})
+    # pre-allocated gatherer: equal shards (no padding) and ragged shards, called twice (buffers are reused)
+    for n_items in (8, 7):
+        g = ResultGatherer(n_items, 16, "cpu")
+        b = n_items // world * rank + min(rank, n_items % world)
+        e = b + n_items // world + (1 if rank < n_items % world else 0)
+        for rep in range(2):
+            local = torch.arange(b, e, dtype=torch.uint8).reshape(-1, 1).repeat(1, 16) + rep
+            allrec = g.gather(local)
+            assert allrec.shape == (n_items, 16)
+            assert torch.equal(allrec[:, 0], torch.arange(n_items, dtype=torch.uint8) + rep)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partial_map_gather_carries_keys_sums_and_counts(tmp_path):
+    world = 2
+    port = 31000 + os.getpid() % 2000
+    mp.spawn(_map_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [np.load(tmp_path / f"map{r}.npz") for r in range(world)]
+    for r in range(world):
+        n = 3 + 2 * r
+        for o in outs:  # identical on every rank
+            np.testing.assert_array_equal(o[f"k{r}"], np.array([[r, i, -i] for i in range(n)], np.int32))
+            np.testing.assert_array_equal(o[f"s{r}"], np.array([[r + 0.5, i, 2.0 * i, i + 1] for i in range(n)]))

@@ -51,6 +51,23 @@ def test_drain_pending_batches_without_blocking():
     assert drain_pending(q, 8, 0.5) == [3, 4]
 
 
+def test_drain_pending_batches_large_records_still_in_the_feeder_pipe():
+    """A scan record (49,152 x 3 float32 = 590 KB) is larger than the queue's pipe, so the records of a backlog
+    are never all 'already there': the dequeue must linger for the feeder thread (the round-1 version used
+    get_nowait() for items 2..n and never batched on a fast box)."""
+    q = multiprocessing.Queue()
+    recs = [np.full((49152, 3), float(i), np.float32) for i in range(6)]
+    for r in recs:
+        q.put(r)
+    got = drain_pending(q, 4, first_timeout=2.0, linger=0.5)
+    assert [int(g[0, 0]) for g in got] == [0, 1, 2, 3]
+    got = drain_pending(q, 4, first_timeout=2.0, linger=0.05)
+    assert [int(g[0, 0]) for g in got] == [4, 5]
+    t0 = time.time()
+    assert drain_pending(q, 4, first_timeout=0.01, linger=0.5) == []  # nothing queued: only first_timeout is spent
+    assert time.time() - t0 < 0.3
+
+
 def test_publish_latest_replaces_stale_map_and_never_blocks():
     dt = DataTransfer()
     t0 = time.time()
