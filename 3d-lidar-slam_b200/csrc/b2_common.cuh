@@ -42,7 +42,7 @@ enum WsSlot : int {
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
     WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_SCAN_COUNT, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D,
-    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_NUM_SLOTS
+    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_ICP_DENSE, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu

@@ -18,6 +18,8 @@
 //   b2_icp_solve.cuh    the per-step solve
 //   b2_icp_group.cuh    icp_iter_kernel: four lanes per query, probes in parallel (dense map, single pairs)
 //   b2_icp_sweep.cuh    icp_sweep_kernel: one thread per query, pruned walk (batches on pair / slab grids)
+//   b2_icp_dense.cuh    icp_dense_kernel: the streaming path (dense resident map): redundant fold + solve per CTA,
+//                       no ticket / last-CTA tail
 //   b2_icp_persist.cuh  persistent driver — experiment, only built with -DB2_EXPERIMENTS (B2_EXPERIMENTS=1 build)
 //   this file           launchers, the driver choice, the chained-launch / WHILE-node loop (icp_run)
 //
@@ -40,6 +42,7 @@ constexpr unsigned kFull = 0xffffffffu;
 #include "b2_icp_solve.cuh"
 #include "b2_icp_group.cuh"
 #include "b2_icp_sweep.cuh"
+#include "b2_icp_dense.cuh"
 #ifdef B2_EXPERIMENTS
 #include "b2_icp_persist.cuh"  // opt-in persistent driver (measured slower inside the captured scan step)
 #endif
@@ -92,6 +95,24 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                        (const CellEntry*)g.entries, g.mask, (const float4*)g.pts, (const VoxEntry*)g.vox,
                        (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets, res, corr, ndone, d2_out,
                        search_only, loop_handle, spread_partial);
+}
+
+void launch_dense(Context* c, dim3 grid, const float4* src, const int* ns_dev, int ns_max, const GridView& g,
+                  const IcpParams& prm, DenseState* states, long long* seqw, double* partial, IcpResultDev* res, int* corr,
+                  int* ndone, double* d2_out, int step, cudaStream_t stream, unsigned long long loop_handle) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool no_pdl = getenv("B2_NO_PDL") != nullptr;
+    cfg.attrs = attr;
+    cfg.numAttrs = no_pdl ? 0 : 1;
+    cudaLaunchKernelEx(&cfg, icp_dense_kernel<2>, src, ns_dev, ns_max, (const VoxEntry*)g.vox, g.mask,
+                       (const GridMeta*)g.meta, prm, states, seqw, partial, res, corr, ndone, d2_out, step, loop_handle);
 }
 
 template <int MODE, int KIND, int L>
@@ -274,15 +295,23 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         gx = div_up(ns_max, 8);
         if (gx > kCtasPerSm * kSMs) gx = kCtasPerSm * kSMs;
     }
+    // the streaming path (one scan against the dense map, point-to-point) has its own step kernel
+    static const bool dense_v1 = getenv("B2_DENSE_V1") != nullptr;  // A/B: the round-1 ticket / last-CTA kernel
+    const bool dense = grid.is_map == 2 && prm.mode == 0 && n_pairs == 1 && !src_offsets && !search_only && !dense_v1;
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
-    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs);
+    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs * 2);
     B2_WS(c, tickets, int, WS_ICP_TICKET, sizeof(int) * ((size_t)n_pairs + 1));
+    B2_WS(c, dstates, DenseState, WS_ICP_DENSE, sizeof(DenseState) * 2 + sizeof(long long));
+    long long* seqw = reinterpret_cast<long long*>(dstates + 2);
     int* ndone = tickets + n_pairs;
-    icp_init_kernel<<<div_up(n_pairs, 128), 128, 0, c->stream>>>(src, src_offsets, ns_dev, ns_max, init_dev, 16,
-                                                                 states, tickets, ndone, n_pairs);
+    if (dense)
+        icp_dense_init_kernel<<<1, 1, 0, c->stream>>>(src, ns_dev, ns_max, init_dev, dstates, seqw, ndone);
+    else
+        icp_init_kernel<<<div_up(n_pairs, 128), 128, 0, c->stream>>>(src, src_offsets, ns_dev, ns_max, init_dev, 16,
+                                                                     states, tickets, ndone, n_pairs);
     B2_LAUNCH_CHECK(c);
     dim3 g(gx, n_pairs);
-    const int launches = search_only ? 1 : prm.max_iter + 1;
+    const int launches = search_only ? 1 : prm.max_iter + 1 + (dense ? 1 : 0);
 #ifdef B2_EXPERIMENTS
     // (opt-in: on B200 the software grid barrier + solve of a step costs more than a kernel boundary)
     static const bool persist = getenv("B2_PERSIST") != nullptr;
@@ -336,7 +365,12 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     const int while_mode = while_env ? atoi(while_env) : -1;
     const bool can_while = c->capturing && n_pairs == 1 && !sweep && !search_only && !corr_out && !d2_out && while_mode != 0;
     const int chained = !can_while ? launches : (while_mode == 1 ? 0 : (launches > kChainSteps ? kChainSteps : launches));
-    auto launch_one = [&](cudaStream_t launch_stream, unsigned long long loop_handle) {
+    auto launch_one = [&](cudaStream_t launch_stream, unsigned long long loop_handle, int step) {
+        if (dense) {
+            launch_dense(c, g, src, ns_dev, ns_max, grid, prm, dstates, seqw, partial, results_dev, corr_out, ndone,
+                         d2_out, step, launch_stream, loop_handle);
+            return;
+        }
 #define B2_ICP_LAUNCH(M, K)                                                                                   \
     launch_iter<M, K>(c, g, src, src_offsets, ns_dev, ns_max, grid, tgt_normals, tgt_offsets, prm, states, partial, \
                       tickets, results_dev, corr_out, ndone, d2_out, search_only, launch_stream, loop_handle)
@@ -373,7 +407,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
 #undef B2_SWEEP4_BRANCH
     };
     for (int it = 0; it < chained; ++it) {
-        launch_one(c->stream, 0ull);
+        launch_one(c->stream, 0ull, it);
         B2_LAUNCH_CHECK(c);
         if (timing) cudaEventRecord(evs[it + 1], c->stream);
         if (check_every > 0 && !search_only && !timing && (it + 1) % check_every == 0 && it + 1 < launches) {
@@ -400,7 +434,7 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         // the body is captured through the copy stream (capture only: nothing runs on that stream)
         B2_CUDA_OK(c, cudaStreamBeginCaptureToGraph(c->copy_stream, np.conditional.phGraph_out[0], nullptr, nullptr, 0,
                                                     cudaStreamCaptureModeThreadLocal));
-        launch_one(c->copy_stream, (unsigned long long)handle);
+        launch_one(c->copy_stream, (unsigned long long)handle, -1);
         cudaGraph_t body = nullptr;
         cudaError_t e = cudaStreamEndCapture(c->copy_stream, &body);
         B2_LAUNCH_CHECK(c);
@@ -417,7 +451,24 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         }
         fprintf(stderr, "\n");
 #ifdef B2_TAIL_TIMING
-        {
+        if (dense) {
+            static unsigned long long h[64 * 148 * 8];
+            cudaMemcpyFromSymbol(h, g_dense_ts, sizeof(h));
+            const char* names[6] = {"entry", "waited", "folded", "solved", "searched", "exit"};
+            for (int jj = 2; jj < 8 && jj < launches; ++jj) {
+                unsigned long long t0 = ~0ull;
+                for (int b = 0; b < gx; ++b) if (h[(jj * 148 + b) * 8] < t0) t0 = h[(jj * 148 + b) * 8];
+                unsigned long long prev_exit = 0;
+                for (int b = 0; b < gx; ++b) if (h[((jj - 1) * 148 + b) * 8 + 5] > prev_exit) prev_exit = h[((jj - 1) * 148 + b) * 8 + 5];
+                fprintf(stderr, "[b2 dense launch %d] first entry %+lld ns after last exit of the previous launch |", jj, (long long)t0 - (long long)prev_exit);
+                for (int k = 0; k < 6; ++k) {
+                    unsigned long long mn = ~0ull, mx = 0, sum = 0;
+                    for (int b = 0; b < gx; ++b) { unsigned long long v = h[(jj * 148 + b) * 8 + k] - t0; if (v < mn) mn = v; if (v > mx) mx = v; sum += v; }
+                    fprintf(stderr, " %s %llu/%llu/%llu", names[k], mn, sum / gx, mx);
+                }
+                fprintf(stderr, "  (min/mean/max ns over CTAs)\n");
+            }
+        } else {
             static unsigned long long h[8 + 2 * 1024];
             cudaMemcpyFromSymbol(h, g_tail_ts, sizeof(h));
             unsigned long long t0 = ~0ull, tmain_min = ~0ull, tmain_max = 0, tstart_max = 0;

@@ -187,6 +187,65 @@ __device__ __forceinline__ bool polar_rotation(double a, double b, double c, dou
     return true;
 }
 
+// Umeyama rotation by Newton's method on SO(3), started at the identity.  The rotation maximises
+// f(R) = tr(R^T C); with M = R^T C, S = sym(M) and a = axial(M - M^T), the second-order model of
+// f(R exp[w]) is tr(M) + a.w - w^T (tr(S) I - S) w / 2, so the Newton step solves H w = a, H = tr(S) I - S, and
+// R is retracted along the Cayley map (an exact rotation, equal to exp[w] to second order — the quadratic
+// convergence is kept; one division per step serves both the 3x3 solve and the map).  An ICP update is a small
+// rotation (1e-2 rad early, 1e-5 late), so two to four steps reach 1e-16 where the scaled polar iteration needs
+// six to eight from a general matrix.  H positive definite at the fixed point is exactly the condition for
+// the GLOBAL maximum over SO(3) (its eigenvalues are the pairwise sums of the signed singular values), i.e.
+// for U diag(1,1,det(UV^T)) V^T, reflections included; anything else — H not positive definite, no
+// convergence — returns false and the caller takes the polar / Jacobi path.
+__device__ __forceinline__ bool procrustes_newton(const double C[9], double R[9]) {
+    double r0 = 1, r1 = 0, r2 = 0, r3 = 0, r4 = 1, r5 = 0, r6 = 0, r7 = 0, r8 = 1;
+    double m0 = C[0], m1 = C[1], m2 = C[2], m3 = C[3], m4 = C[4], m5 = C[5], m6 = C[6], m7 = C[7], m8 = C[8];
+    const double scale2 = m0 * m0 + m1 * m1 + m2 * m2 + m3 * m3 + m4 * m4 + m5 * m5 + m6 * m6 + m7 * m7 + m8 * m8;
+    if (!(scale2 > 0.0) || !isfinite(scale2)) return false;
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        const double tr = m0 + m4 + m8;
+        // H = tr(S) I - S (symmetric), S = (M + M^T) / 2
+        const double h00 = tr - m0, h11 = tr - m4, h22 = tr - m8;
+        const double h01 = -0.5 * (m1 + m3), h02 = -0.5 * (m2 + m6), h12 = -0.5 * (m5 + m7);
+        const double a0 = m7 - m5, a1 = m2 - m6, a2 = m3 - m1;
+        // adjugate of H and Sylvester's criterion
+        const double c00 = h11 * h22 - h12 * h12, c01 = h02 * h12 - h01 * h22, c02 = h01 * h12 - h02 * h11;
+        const double c11 = h00 * h22 - h02 * h02, c12 = h01 * h02 - h00 * h12, c22 = h00 * h11 - h01 * h01;
+        const double det = h00 * c00 + h01 * c01 + h02 * c02;
+        // (relative thresholds: a rank-deficient covariance must go to the SVD path, not through a tiny pivot)
+        if (!(h00 > 1e-9 * tr) || !(c22 > 1e-9 * tr * tr) || !(det > 1e-9 * tr * tr * tr)) return false;
+        // v = adj(H) a = det * w ;  u = w / 2 = v / (2 det) ;  Q = I + (4 det [v] + 2 [v]^2) / (4 det^2 + |v|^2)
+        const double v0 = c00 * a0 + c01 * a1 + c02 * a2;
+        const double v1 = c01 * a0 + c11 * a1 + c12 * a2;
+        const double v2 = c02 * a0 + c12 * a1 + c22 * a2;
+        const double vv = v0 * v0 + v1 * v1 + v2 * v2;
+        const double d4 = 4.0 * det * det;
+        const double inv = 1.0 / (d4 + vv);
+        const double ka = 4.0 * det * inv, kb = 2.0 * inv;
+        // [v]^2 = v v^T - |v|^2 I
+        const double q0 = 1.0 + kb * (v0 * v0 - vv), q4 = 1.0 + kb * (v1 * v1 - vv), q8 = 1.0 + kb * (v2 * v2 - vv);
+        const double q1 = kb * v0 * v1 - ka * v2, q3 = kb * v0 * v1 + ka * v2;
+        const double q2 = kb * v0 * v2 + ka * v1, q6 = kb * v0 * v2 - ka * v1;
+        const double q5 = kb * v1 * v2 - ka * v0, q7 = kb * v1 * v2 + ka * v0;
+        // R <- R Q
+        const double n0 = r0 * q0 + r1 * q3 + r2 * q6, n1 = r0 * q1 + r1 * q4 + r2 * q7, n2 = r0 * q2 + r1 * q5 + r2 * q8;
+        const double n3 = r3 * q0 + r4 * q3 + r5 * q6, n4 = r3 * q1 + r4 * q4 + r5 * q7, n5 = r3 * q2 + r4 * q5 + r5 * q8;
+        const double n6 = r6 * q0 + r7 * q3 + r8 * q6, n7 = r6 * q1 + r7 * q4 + r8 * q7, n8 = r6 * q2 + r7 * q5 + r8 * q8;
+        r0 = n0; r1 = n1; r2 = n2; r3 = n3; r4 = n4; r5 = n5; r6 = n6; r7 = n7; r8 = n8;
+        // |w|^2 = |v|^2 / det^2: below 1e-16 the step just applied leaves an error of ~|w|^2 (quadratic)
+        if (vv < 1e-16 * det * det) {
+            R[0] = r0; R[1] = r1; R[2] = r2; R[3] = r3; R[4] = r4; R[5] = r5; R[6] = r6; R[7] = r7; R[8] = r8;
+            return true;
+        }
+        // M <- R^T C
+        m0 = r0 * C[0] + r3 * C[3] + r6 * C[6]; m1 = r0 * C[1] + r3 * C[4] + r6 * C[7]; m2 = r0 * C[2] + r3 * C[5] + r6 * C[8];
+        m3 = r1 * C[0] + r4 * C[3] + r7 * C[6]; m4 = r1 * C[1] + r4 * C[4] + r7 * C[7]; m5 = r1 * C[2] + r4 * C[5] + r7 * C[8];
+        m6 = r2 * C[0] + r5 * C[3] + r8 * C[6]; m7 = r2 * C[1] + r5 * C[4] + r8 * C[7]; m8 = r2 * C[2] + r5 * C[5] + r8 * C[8];
+    }
+    return false;
+}
+
 // Evaluate one A.3 loop step from the reduced sums.  Runs on one thread; written so that every
 // small matrix stays in registers (a single GPU thread retires roughly one dependent instruction
 // per 6-10 cycles, so the instruction count of this tail is what the iteration latency is made of).
@@ -230,7 +289,8 @@ __device__ __noinline__ void icp_step(const double* S, int ns, const IcpParams p
             C[0] = S[6] * inv - mq0 * mp0;  C[1] = S[7] * inv - mq0 * mp1;  C[2] = S[8] * inv - mq0 * mp2;
             C[3] = S[9] * inv - mq1 * mp0;  C[4] = S[10] * inv - mq1 * mp1; C[5] = S[11] * inv - mq1 * mp2;
             C[6] = S[12] * inv - mq2 * mp0; C[7] = S[13] * inv - mq2 * mp1; C[8] = S[14] * inv - mq2 * mp2;
-            if (!polar_rotation(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], R))
+            if (!procrustes_newton(C, R) &&
+                !polar_rotation(C[0], C[1], C[2], C[3], C[4], C[5], C[6], C[7], C[8], R))
                 rotation_from_covariance(C, R);
             const double p0 = cur.pivot[0], p1 = cur.pivot[1], p2 = cur.pivot[2];
             mp0 += p0; mp1 += p1; mp2 += p2;

@@ -61,17 +61,17 @@ def test_scan_step_widens_its_sort_budget_instead_of_failing(b2):
     origin = [-100.0, -100.0, -100.0]
     eng.map_init(0.05, origin, 0.05, 1 << 18)
     prm = b2.make_params(0.05, 5)
-    for s in scans:                      # first scan: fuse only; then eager, captured and replayed steps
+    poses = []
+    for s in scans + scans:              # first scan: fuse only; then eager, captured and replayed steps
         res = eng.slam_scan(s, 0.02, prm)
-    for s in scans:
-        res = eng.slam_scan(s, 0.02, prm)
+        poses.append(res.matrix())
     assert res.fitness > 0.9             # the last scans register against their own earlier copies
     _, keys = eng.map_export()
     want = set()
-    for s in scans:                      # (poses stay within 1e-3 of identity: compare the occupancy coarsely)
-        want |= {tuple(k) for k in orc.voxel_keys(f64(s), 0.05, origin=np.array(origin)).tolist()}
+    for s, T in zip(scans + scans, poses):
+        want |= {tuple(k) for k in orc.voxel_keys(orc.transform(f64(s), T), 0.05, origin=np.array(origin)).tolist()}
     got = {tuple(k) for k in keys.cpu().numpy().tolist()}
-    assert len(got ^ want) <= len(want) // 50
+    assert len(got ^ want) <= 3          # (a point within rounding of a voxel face may flip)
     eng.close()
 
 
