@@ -182,14 +182,20 @@ struct __align__(16) CellEntry {
 };
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 
-// Resident map with one voxel per cell (voxel edge == search radius, e.g. 5 cm / 5 cm): the centroid
-// lives INSIDE the hash entry, so a stencil probe is a single 32-byte sector and there is no second,
-// dependent load of the point.
-struct __align__(32) VoxEntry {
-    unsigned long long key;  // kEmptyKey = vacant
-    float x, y, z;           // voxel centroid (float32 of sum/n)
-    unsigned int n;          // points merged into the voxel (0 while the slot is being created)
-    unsigned int pad[2];
+// Resident map with one voxel per cell (voxel edge == search radius, e.g. 5 cm / 5 cm, BASELINE config 2):
+// brick-major and directly indexed.  The hash holds BRICKS of 8 x 8 x 8 voxels (one 16-byte record per brick);
+// a brick is a dense array of 512 float4 cells (centroid x, y, z; w = bit pattern of the int32 point count,
+// 0 = empty), z fastest, so the three z-neighbours of a stencil row are 48 contiguous bytes, a 128-byte line
+// holds eight consecutive cells, and a whole 27-cell stencil touches 1-8 bricks instead of 27 random hash
+// slots.  Bricks are allocated from a pool in creation order (scans arrive along a trajectory, so the
+// bricks one scan reads are neighbours in memory as well).
+constexpr int kBrickEdge = 8;
+constexpr int kBrickCells = kBrickEdge * kBrickEdge * kBrickEdge;  // 512
+constexpr unsigned kNoBrick = 0xFFFFFFFFu;
+struct __align__(16) BrickEntry {
+    unsigned long long key;  // map_cell_key(brick x, y, z); kEmptyKey = vacant
+    unsigned index;          // brick number in the pool (kNoBrick while being created / pool exhausted)
+    unsigned pad;
 };
 
 struct GridMeta {
@@ -323,25 +329,23 @@ __device__ __forceinline__ void ldg256(const void* p, unsigned long long& a, uns
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
 }
 
-// Probe the dense voxel table: on a hit returns true and the centroid + slot of the voxel.
-__device__ __forceinline__ bool vox_lookup(const VoxEntry* __restrict__ tab, unsigned mask, unsigned long long key,
-                                           float& x, float& y, float& z, unsigned& slot) {
+// Probe the brick table: the brick's pool index, or kNoBrick.
+__device__ __forceinline__ unsigned brick_lookup(const BrickEntry* __restrict__ tab, unsigned mask,
+                                                 unsigned long long key) {
     unsigned h = cell_hash(key) & mask;
 #pragma unroll 1
     for (unsigned probe = 0; probe <= mask; ++probe) {
-        unsigned long long k, xy, zn, pad;
-        ldg256(tab + h, k, xy, zn, pad);
-        if (k == key) {
-            x = __uint_as_float((unsigned)xy);
-            y = __uint_as_float((unsigned)(xy >> 32));
-            z = __uint_as_float((unsigned)zn);
-            slot = h;
-            return (unsigned)(zn >> 32) != 0u;
-        }
-        if (k == kEmptyKey) return false;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(tab + h));
+        const unsigned long long k = ((unsigned long long)raw.y << 32) | raw.x;
+        if (k == key) return raw.z;
+        if (k == kEmptyKey) return kNoBrick;
         h = (h + 1) & mask;
     }
-    return false;
+    return kNoBrick;
+}
+// cell number inside a brick: z fastest
+__device__ __forceinline__ unsigned brick_local(int x, int y, int z) {
+    return ((unsigned)(x & 7) << 6) | ((unsigned)(y & 7) << 3) | (unsigned)(z & 7);
 }
 
 #endif  // __CUDACC__
@@ -393,8 +397,9 @@ struct GridView {
     unsigned mask;        // capacity - 1
     float4* pts;          // cell-sorted copy, w = original (per-cloud) index
     GridMeta* meta;       // [n_clouds]
-    int is_map;           // 0: pair grid, 1: resident map with slabs (brick > 1), 2: dense resident map (vox)
-    VoxEntry* vox;        // is_map == 2
+    int is_map;           // 0: pair grid, 1: resident map with slabs (brick > 1), 2: dense resident map (bricks)
+    BrickEntry* btab;     // is_map == 2: brick hash (mask = its capacity - 1), cells = pts
+    unsigned pool_bricks; // is_map == 2: bricks in the pool
 };
 int grid_build(Context* c, const float4* pts, int n_max, const int* n_dev, const int* cloud_offsets, int n_clouds,
                double cell, int slot_base, GridView* out);

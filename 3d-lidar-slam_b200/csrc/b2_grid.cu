@@ -100,7 +100,8 @@ int grid_build(Context* c, const float4* pts, int n_max, const int* n_dev, const
     out->pts = gpts;
     out->meta = meta;
     out->is_map = 0;
-    out->vox = nullptr;
+    out->btab = nullptr;
+    out->pool_bricks = 0;
     return B2_OK;
 }
 

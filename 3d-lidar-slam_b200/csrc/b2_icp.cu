@@ -92,8 +92,7 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
     cfg.numAttrs = no_pdl ? 0 : 1;
     static const int spread_partial = getenv("B2_SPREAD_PARTIAL") ? atoi(getenv("B2_SPREAD_PARTIAL")) : 0;  // experiment
     cudaLaunchKernelEx(&cfg, icp_iter_kernel<MODE, IS_MAP>, src, src_offs, ns_dev, ns_max,
-                       (const CellEntry*)g.entries, g.mask, (const float4*)g.pts, (const VoxEntry*)g.vox,
-                       (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets, res, corr, ndone, d2_out,
+                       (const CellEntry*)g.entries, g.mask, (const float4*)g.pts, (const GridMeta*)g.meta, nrm, tgt_offs, prm, st, partial, tickets, res, corr, ndone, d2_out,
                        search_only, loop_handle, spread_partial);
 }
 
@@ -111,8 +110,8 @@ void launch_dense(Context* c, dim3 grid, const float4* src, const int* ns_dev, i
     static const bool no_pdl = getenv("B2_NO_PDL") != nullptr;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    cudaLaunchKernelEx(&cfg, icp_dense_kernel<2>, src, ns_dev, ns_max, (const VoxEntry*)g.vox, g.mask,
-                       (const GridMeta*)g.meta, prm, states, seqw, partial, res, corr, ndone, d2_out, step, loop_handle);
+    cudaLaunchKernelEx(&cfg, icp_dense_kernel, src, ns_dev, ns_max, (const BrickEntry*)g.btab, g.mask,
+                       (const float4*)g.pts, (const GridMeta*)g.meta, prm, states, seqw, partial, res, corr, ndone, d2_out, step, loop_handle);
 }
 
 template <int MODE, int KIND, int L>
@@ -140,7 +139,8 @@ void launch_sweep(Context* c, dim3 grid, const float4* src, const int* src_offs,
 // Candidate census of the 27-cell stencil (the data-dependent term of the byte model); kind as in GridView.
 __global__ void __launch_bounds__(256)
 stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __restrict__ T,
-                     const CellEntry* __restrict__ entries, const VoxEntry* __restrict__ vox, unsigned mask,
+                     const CellEntry* __restrict__ entries, const BrickEntry* __restrict__ btab, unsigned mask,
+                     const float4* __restrict__ cells,
                      const GridMeta* __restrict__ meta, int kind, unsigned long long* __restrict__ total) {
     const int lane = threadIdx.x & 31;
     const int q = (blockIdx.x * 256 + threadIdx.x) >> 5;
@@ -169,9 +169,9 @@ stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __res
         } else {
             const unsigned long long key = map_cell_key(nx, ny, nz);
             if (kind == 2) {
-                float x, y, z;
-                unsigned slot;
-                cnt = vox_lookup(vox, mask, key, x, y, z, slot) ? 1u : 0u;
+                const unsigned bi = brick_lookup(btab, mask, map_cell_key(nx >> 3, ny >> 3, nz >> 3));
+                if (bi != kNoBrick)
+                    cnt = __float_as_int(__ldg(cells + (size_t)bi * kBrickCells + brick_local(nx, ny, nz)).w) != 0 ? 1u : 0u;
             } else {
                 const CellEntry e = grid_lookup(entries, mask, key);
                 if (e.key == key) cnt = e.cnt;
@@ -186,8 +186,8 @@ stencil_count_kernel(const float4* __restrict__ src, int ns, const double* __res
 
 int map_stencil_count(Context* c, const float4* src, int ns, const double* T_dev, const GridView& g,
                       unsigned long long* total_dev) {
-    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.vox,
-                                                                                  g.mask, g.meta, g.is_map, total_dev);
+    stencil_count_kernel<<<div_up((long long)ns * 32, 256), 256, 0, c->stream>>>(src, ns, T_dev, g.entries, g.btab,
+                                                                                  g.mask, g.pts, g.meta, g.is_map, total_dev);
     B2_LAUNCH_CHECK(c);
     return B2_OK;
 }
@@ -214,11 +214,10 @@ int launch_persist(Context* c, const float4* src, const int* ns_dev, int ns_max,
     const CellEntry* entries = g.entries;
     unsigned mask = g.mask;
     const float4* gpts = g.pts;
-    const VoxEntry* vox = g.vox;
     const GridMeta* meta = g.meta;
     IcpParams prm_v = prm;
     void* args[] = {(void*)&src, (void*)&ns_dev, (void*)&ns_max, (void*)&entries, (void*)&mask, (void*)&gpts,
-                    (void*)&vox, (void*)&meta, (void*)&nrm, (void*)&prm_v, (void*)&st, (void*)&partial,
+                    (void*)&meta, (void*)&nrm, (void*)&prm_v, (void*)&st, (void*)&partial,
                     (void*)&psync, (void*)&res, (void*)&corr, (void*)&ndone};
     B2_CUDA_OK(c, cudaLaunchCooperativeKernel((const void*)icp_persist_kernel<MODE, KIND>, dim3(grid), dim3(kThreads),
                                               args, 0, c->stream));
@@ -296,8 +295,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         if (gx > kCtasPerSm * kSMs) gx = kCtasPerSm * kSMs;
     }
     // the streaming path (one scan against the dense map, point-to-point) has its own step kernel
-    static const bool dense_v1 = getenv("B2_DENSE_V1") != nullptr;  // A/B: the round-1 ticket / last-CTA kernel
-    const bool dense = grid.is_map == 2 && prm.mode == 0 && n_pairs == 1 && !src_offsets && !search_only && !dense_v1;
+    const bool dense = grid.is_map == 2;
+    if (dense && (prm.mode != 0 || n_pairs != 1 || src_offsets || search_only))
+        return set_error(c, B2_ERR_INVALID, "the dense resident map registers one point-to-point scan at a time");
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
     B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs * 2);
     B2_WS(c, tickets, int, WS_ICP_TICKET, sizeof(int) * ((size_t)n_pairs + 1));
@@ -315,18 +315,16 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
 #ifdef B2_EXPERIMENTS
     // (opt-in: on B200 the software grid barrier + solve of a step costs more than a kernel boundary)
     static const bool persist = getenv("B2_PERSIST") != nullptr;
-    if (persist && n_pairs == 1 && !src_offsets && !search_only && !d2_out && !c->capturing) {
+    if (persist && grid.is_map != 2 && n_pairs == 1 && !src_offsets && !search_only && !d2_out && !c->capturing) {
         // single registration: one cooperative launch runs the whole A.3 loop
         B2_WS(c, psync, PersistSync, WS_ICP_SYNC, sizeof(PersistSync));
         B2_CUDA_OK(c, cudaMemsetAsync(psync, 0, sizeof(PersistSync), c->stream));
         int rc = B2_OK;
         if (prm.mode == 0) {
-            if (grid.is_map == 2) rc = launch_persist<0, 2>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
-            else if (grid.is_map == 1) rc = launch_persist<0, 1>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
+            if (grid.is_map == 1) rc = launch_persist<0, 1>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
             else rc = launch_persist<0, 0>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
         } else {
-            if (grid.is_map == 2) rc = launch_persist<1, 2>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
-            else if (grid.is_map == 1) rc = launch_persist<1, 1>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
+            if (grid.is_map == 1) rc = launch_persist<1, 1>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
             else rc = launch_persist<1, 0>(c, src, ns_dev, ns_max, grid, tgt_normals, prm, states, partial, psync, results_dev, corr_out, ndone);
         }
 #ifdef B2_TAIL_TIMING
@@ -390,14 +388,12 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
                                   partial, tickets, results_dev, corr_out, ndone, d2_out, search_only);       \
     } while (0)
         if (prm.mode == 0) {
-            if (grid.is_map == 2) B2_ICP_LAUNCH(0, 2);
-            else if (!sweep && grid.is_map == 1) B2_ICP_LAUNCH(0, 1);
+            if (!sweep && grid.is_map == 1) B2_ICP_LAUNCH(0, 1);
             else if (!sweep) B2_ICP_LAUNCH(0, 0);
             else if (grid.is_map == 1) B2_ICP_SWEEP(0, 1);
             else B2_ICP_SWEEP(0, 0);
         } else {
-            if (grid.is_map == 2) B2_ICP_LAUNCH(1, 2);
-            else if (!sweep && grid.is_map == 1) B2_ICP_LAUNCH(1, 1);
+            if (!sweep && grid.is_map == 1) B2_ICP_LAUNCH(1, 1);
             else if (!sweep) B2_ICP_LAUNCH(1, 0);
             else if (grid.is_map == 1) B2_ICP_SWEEP(1, 1);
             else B2_ICP_SWEEP(1, 0);

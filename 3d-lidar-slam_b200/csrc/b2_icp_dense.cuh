@@ -114,12 +114,132 @@ __device__ __noinline__ bool icp_step_local(const double* S, int ns, const IcpPa
     return false;
 }
 
+// ---- correspondence search against the brick-major map -------------------------------------------------
+// A warp serves eight queries per round, four lanes each (21.8 k queries = one round over 148 x 160 groups).
+// Round 1's search was bound by instruction issue (2.9 M warp instructions per step: every lane hashed and
+// probed its own 7 stencil cells, and the group leader alone transformed the point and accumulated the 17
+// sums while three lanes idled).  Here the work of a query is spread evenly over its four lanes:
+//   * lanes 0-2 each compute ONE axis of P = T p and of the query's cell (one IEEE division each);
+//   * the 27-cell stencil lies in at most 2 x 2 x 2 bricks: lane g looks up the two corner bricks (y, z) = (g>>1,
+//     g&1) — 2 hash probes per lane instead of 7, shared by shuffles;
+//   * cell c = g + 4k of the stencil is then a directly indexed 16-byte load (all 7 of a lane in flight at once),
+//     an emptiness test on the count in w and an un-fused fp64 distance — no key compare, no probe chain;
+//   * arg-min over the group is a 2-step butterfly on (d2, stencil cell number): ties go to the lexicographically
+//     smallest voxel key, i.e. the lowest index of the canonical (key-ordered) export, as in the oracle;
+//   * the 17 normal-equation terms are added by all four lanes (5 / 4 / 4 / 4 terms) to the group's column.
+struct DenseArgs {
+    const BrickEntry* btab;
+    unsigned bmask;
+    const float4* cells;
+    double r2;
+    int* corr_out;
+    double* d2_out;
+};
+
+__device__ __forceinline__ void dense_search_round(const DenseArgs& a, const double* __restrict__ sT,
+                                                   const double* __restrict__ sPivot, const GridMeta& meta, float4 p,
+                                                   bool valid, int q, double (*sAccL)[kLeaders], int col) {
+    const int lane = threadIdx.x & 31;
+    const int g = lane & (kGroup - 1);
+    const int lead = lane & ~(kGroup - 1);
+    // ---- P = T p and the query's cell: axis g on lane g ------------------------------------------------
+    const float pxf = __shfl_sync(kFull, p.x, lead), pyf = __shfl_sync(kFull, p.y, lead), pzf = __shfl_sync(kFull, p.z, lead);
+    valid = __shfl_sync(kFull, (int)valid, lead) != 0;
+    double Pa = 0.0;
+    int ca = 0;
+    if (g < 3) {
+        const double* row = sT + 4 * g;
+        Pa = dadd(dadd(dadd(dmul(row[0], (double)pxf), dmul(row[1], (double)pyf)), dmul(row[2], (double)pzf)), row[3]);
+        ca = voxel_coord(Pa, meta.origin[g], meta.cell);
+    }
+    const double Px = __shfl_sync(kFull, Pa, lead), Py = __shfl_sync(kFull, Pa, lead + 1), Pz = __shfl_sync(kFull, Pa, lead + 2);
+    const int cx = __shfl_sync(kFull, ca, lead), cy = __shfl_sync(kFull, ca, lead + 1), cz = __shfl_sync(kFull, ca, lead + 2);
+    const int lim = (1 << 20) - 10;
+    const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
+    const bool live = valid && in_range;  // (a query outside the key space has no neighbour)
+
+    // ---- the (up to) eight bricks under the stencil ------------------------------------------------------
+    const int bx0 = (cx - 1) >> 3, by0 = (cy - 1) >> 3, bz0 = (cz - 1) >> 3;
+    const int bx1 = (cx + 1) >> 3;
+    unsigned idx0 = kNoBrick, idx1 = kNoBrick;
+    if (live) {
+        const int by = (g & 2) ? (cy + 1) >> 3 : by0, bz = (g & 1) ? (cz + 1) >> 3 : bz0;
+        idx0 = brick_lookup(a.btab, a.bmask, map_cell_key(bx0, by, bz));
+        idx1 = bx1 == bx0 ? idx0 : brick_lookup(a.btab, a.bmask, map_cell_key(bx1, by, bz));
+    }
+    // ---- this lane's cells: all loads in flight before the first distance ----------------------------------
+    float4 t[kCellsPerLane];
+    bool have[kCellsPerLane];
+#pragma unroll
+    for (int k = 0; k < kCellsPerLane; ++k) {
+        const int c = g + kGroup * k;
+        const int c3 = (c * 171) >> 9;  // c / 3 for c < 128
+        const int c9 = (c * 57) >> 9;   // c / 9
+        const int nx = cx + c9 - 1, ny = cy + (c3 - 3 * c9) - 1, nz = cz + (c - 3 * c3) - 1;
+        const int srcl = lead + ((((ny >> 3) != by0) ? 2 : 0) | (((nz >> 3) != bz0) ? 1 : 0));
+        const unsigned i0 = __shfl_sync(kFull, idx0, srcl), i1 = __shfl_sync(kFull, idx1, srcl);
+        const unsigned bi = (nx >> 3) != bx0 ? i1 : i0;
+        have[k] = c < 27 && bi != kNoBrick;
+        if (have[k]) t[k] = __ldg(a.cells + (size_t)bi * kBrickCells + brick_local(nx, ny, nz));
+    }
+    double best = INFINITY;
+    int best_c = 0x7fffffff;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+    for (int k = 0; k < kCellsPerLane; ++k) {
+        if (!have[k] || __float_as_int(t[k].w) == 0) continue;
+        const double d2 = dist2_strict(Px, Py, Pz, (double)t[k].x, (double)t[k].y, (double)t[k].z);
+        if (d2 < best) {  // (cells of a lane come in increasing stencil order: ties keep the earlier one)
+            best = d2;
+            best_c = g + kGroup * k;
+            bx = t[k].x; by = t[k].y; bz = t[k].z;
+        }
+    }
+    // ---- arg-min over the group: (d2, stencil cell) lexicographic ------------------------------------------
+    double gbest = best;
+    int gc = best_c;
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) {
+        const double od = __shfl_xor_sync(kFull, gbest, o);
+        const int oc = __shfl_xor_sync(kFull, gc, o);
+        if (od < gbest || (od == gbest && oc < gc)) {
+            gbest = od;
+            gc = oc;
+        }
+    }
+    const bool found = valid && gbest < a.r2;
+    const int wl = lead + (gc & (kGroup - 1));  // the lane that holds stencil cell gc (meaningful when found)
+    const float Qxf = __shfl_sync(kFull, bx, wl), Qyf = __shfl_sync(kFull, by, wl), Qzf = __shfl_sync(kFull, bz, wl);
+    if (!valid) return;
+    if (g == 0) {
+        if (a.corr_out) a.corr_out[q] = found ? gc : -1;  // (stencil cell number of the neighbour: diagnostic only)
+        if (a.d2_out) a.d2_out[q] = found ? gbest : 0.0;
+    }
+    if (!found) return;
+    // ---- the 17 terms, spread over the four lanes (column `col` belongs to this group) ------------------------
+    const double px = Px - sPivot[0], py = Py - sPivot[1], pz = Pz - sPivot[2];
+    if (g == 0) {
+        sAccL[0][col] += px;
+        sAccL[1][col] += py;
+        sAccL[2][col] += pz;
+        sAccL[15][col] += gbest;
+        sAccL[16][col] += 1.0;
+    } else {
+        const int ax = g - 1;
+        const double qa = (double)(ax == 0 ? Qxf : (ax == 1 ? Qyf : Qzf)) - sPivot[ax];
+        sAccL[3 + ax][col] += qa;
+        sAccL[6 + 3 * ax][col] += qa * px;
+        sAccL[7 + 3 * ax][col] += qa * py;
+        sAccL[8 + 3 * ax][col] += qa * pz;
+    }
+}
+
 // step >= 0: index of this launch in the chain (parity baked in by the host); step < 0: body of a CUDA-graph
 // WHILE node — the launch index is read from *seqw first (one more round trip, only in the tail of long budgets).
-template <int KIND>  // 2: dense voxel table (VoxEntry hash)
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
-                 const VoxEntry* __restrict__ vox, unsigned mask, const GridMeta* __restrict__ metas, IcpParams prm,
+                 const BrickEntry* __restrict__ btab, unsigned bmask, const float4* __restrict__ cells,
+                 const GridMeta* __restrict__ metas, IcpParams prm,
                  DenseState* __restrict__ states, long long* __restrict__ seqw, double* __restrict__ partial,
                  IcpResultDev* __restrict__ results, int* __restrict__ corr_out, int* __restrict__ ndone,
                  double* __restrict__ d2_out, int step, unsigned long long loop_handle) {
@@ -188,12 +308,10 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     const double* sT = sDS.st.T;
     const double* sPivot = sDS.st.pivot;
 
-    SearchArgs a;
-    a.entries = nullptr; a.vox = vox; a.gpts = nullptr; a.tgt_normals = nullptr; a.mask = mask;
-    a.tgt_base = 0;
-    a.pair = 0u;
+    DenseArgs a;
+    a.btab = btab; a.bmask = bmask; a.cells = cells;
     a.r2 = dmul(prm.max_corr, prm.max_corr);
-    a.corr_out = corr_out; a.d2_out = d2_out; a.search_only = 0;
+    a.corr_out = corr_out; a.d2_out = d2_out;
 
     // same dealing of queries as icp_iter_kernel: 160 consecutive queries per CTA and round, the partial last
     // round of a multi-round source in 8-query warp chunks over all CTAs
@@ -207,7 +325,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         float4 p = p_first;
         if (!first && (lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
         first = false;
-        search_round<0, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+        dense_search_round(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
     }
     if (spread) {
         const int q0 = q_end + ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * (32 / kGroup);
@@ -216,7 +334,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
             const bool valid = q < ns;
             float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
             if ((lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
-            search_round<0, KIND>(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+            dense_search_round(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
         }
     }
     __syncthreads();

@@ -39,7 +39,6 @@ constexpr int kLeaders = kThreads / kGroup;  // accumulator columns per CTA
 
 struct SearchArgs {
     const CellEntry* entries;
-    const VoxEntry* vox;
     const float4* gpts;
     const float4* tgt_normals;
     unsigned mask;
@@ -126,32 +125,7 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
                 }
                 hpos[k] = cell_hash(key[k]) & a.mask;
             }
-            if (KIND == 2) {
-                unsigned long long ek[kProbeBatch], exy[kProbeBatch], ezn[kProbeBatch], epad[kProbeBatch];
-#pragma unroll
-                for (int k = 0; k < kProbeBatch; ++k)
-                    if (live[k]) ldg256(a.vox + hpos[k], ek[k], exy[k], ezn[k], epad[k]);
-#pragma unroll
-                for (int k = 0; k < kProbeBatch; ++k) {
-                    if (!live[k]) continue;
-                    unsigned h = hpos[k];
-                    while (ek[k] != key[k] && ek[k] != kEmptyKey) {  // collision chain (rare at load <= 0.5)
-                        h = (h + 1) & a.mask;
-                        ldg256(a.vox + h, ek[k], exy[k], ezn[k], epad[k]);
-                    }
-                    if (ek[k] == key[k] && (unsigned)(ezn[k] >> 32) != 0u) {
-                        const float x = __uint_as_float((unsigned)exy[k]);
-                        const float y = __uint_as_float((unsigned)(exy[k] >> 32));
-                        const float z = __uint_as_float((unsigned)ezn[k]);
-                        const double d2 = dist2_strict(Px, Py, Pz, (double)x, (double)y, (double)z);
-                        if (d2 < best || (d2 == best && (int)h < best_idx)) {
-                            best = d2;
-                            best_idx = (int)h;
-                            bx = x; by = y; bz = z;
-                        }
-                    }
-                }
-            } else {
+            {
                 uint4 raw[kProbeBatch];
 #pragma unroll
                 for (int k = 0; k < kProbeBatch; ++k)
@@ -190,7 +164,7 @@ __device__ __forceinline__ void search_round(const SearchArgs& a, const double* 
             }
         }
     }
-    if (KIND != 2) {
+    {
         // Exact phase.  Let M bound |d2_f32 - d2| for every candidate (rounding of P to float32 plus the
         // float32 arithmetic): every candidate's d2_f32 >= d2* - M, where d2* is the true minimum, so a
         // candidate with d2_f32 > gmin + 2M has d2 > d2* and cannot be the nearest neighbour.  Only the
@@ -329,12 +303,11 @@ __device__ __forceinline__ void grid_fold(const double* __restrict__ partial, in
     __syncthreads();
 }
 
-template <int MODE, int KIND>  // KIND 0: pair grid, 1: resident map with slabs, 2: dense resident map
+template <int MODE, int KIND>  // KIND 0: pair grid, 1: resident map with slabs (the dense map has b2_icp_dense.cuh)
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs, const int* __restrict__ ns_dev,
                 int ns_max, const CellEntry* __restrict__ entries, unsigned mask,
-                const float4* __restrict__ gpts, const VoxEntry* __restrict__ vox,
-                const GridMeta* __restrict__ metas, const float4* __restrict__ tgt_normals,
+                const float4* __restrict__ gpts, const GridMeta* __restrict__ metas, const float4* __restrict__ tgt_normals,
                 const int* __restrict__ tgt_offs, IcpParams prm, IcpState* __restrict__ states,
                 double* __restrict__ partial, int* __restrict__ tickets, IcpResultDev* __restrict__ results,
                 int* __restrict__ corr_out, int* __restrict__ ndone, double* __restrict__ d2_out,
@@ -392,7 +365,7 @@ icp_iter_kernel(const float4* __restrict__ src, const int* __restrict__ src_offs
     const double* sPivot = sState.pivot;
 
     SearchArgs a;
-    a.entries = entries; a.vox = vox; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
+    a.entries = entries; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
     a.tgt_base = tgt_offs ? tgt_offs[pair] : 0;
     a.pair = (unsigned)pair;
     a.r2 = dmul(prm.max_corr, prm.max_corr);

@@ -22,7 +22,7 @@ template <int MODE, int KIND>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
                    const CellEntry* __restrict__ entries, unsigned mask, const float4* __restrict__ gpts,
-                   const VoxEntry* __restrict__ vox, const GridMeta* __restrict__ metas,
+                   const GridMeta* __restrict__ metas,
                    const float4* __restrict__ tgt_normals, IcpParams prm, IcpState* __restrict__ st,
                    double* __restrict__ partial, PersistSync* __restrict__ sync, IcpResultDev* __restrict__ results,
                    int* __restrict__ corr_out, int* __restrict__ ndone) {
@@ -43,7 +43,7 @@ icp_persist_kernel(const float4* __restrict__ src, const int* __restrict__ ns_de
         reinterpret_cast<double*>(&sMeta)[threadIdx.x - 32] = reinterpret_cast<const double*>(metas)[threadIdx.x - 32];
 
     SearchArgs a;
-    a.entries = entries; a.vox = vox; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
+    a.entries = entries; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
     a.tgt_base = 0;
     a.pair = 0u;
     a.r2 = dmul(prm.max_corr, prm.max_corr);

@@ -376,7 +376,7 @@ icp_sweep_kernel(const float4* __restrict__ src, const int* __restrict__ src_off
 
     SearchArgs a;
     a.walk = sWalk;
-    a.entries = entries; a.vox = nullptr; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
+    a.entries = entries; a.gpts = gpts; a.tgt_normals = tgt_normals; a.mask = mask;
     a.tgt_base = tgt_offs ? tgt_offs[pair] : 0;
     a.pair = (unsigned)pair;
     a.r2 = dmul(prm.max_corr, prm.max_corr);

@@ -15,9 +15,12 @@
 //             (first `cnt` slots used), w = slab position  -> what ICP reads.
 //   acc     : [capacity * brick^3] (sum x, sum y, sum z, n) in fp64 -> exact merge.
 //   lut/lid : per-cell voxel-local-id <-> slab-slot maps (bytes).
-//   brick == 1 (voxel edge == search radius, BASELINE config 2): the cell IS the voxel, and the
-//             table degenerates to 32-byte VoxEntry {key, centroid, n} records — a stencil probe of
-//             the ICP kernel is then one LDG.256 with no dependent second load.
+//   brick == 1 (voxel edge == search radius, BASELINE config 2): brick-major, directly indexed.  The hash
+//             holds bricks of 8^3 voxels; a brick is a dense array of 512 float4 cells (z fastest) from a pool
+//             filled in creation order, so a 27-cell stencil is 9 runs of 48 contiguous bytes in 1-8 bricks and
+//             the ICP kernel stages the cells its queries need with coalesced loads (b2_icp_dense.cuh).  Round 1
+//             hashed single voxels into a 1 GiB table of 32-byte records: 27 random sectors per query, and
+//             every probe of a warp in a different 128-byte line — the step was bound by L1 wavefronts.
 //
 // Fusion of a scan = voxel_downsample(T * scan, voxel, origin) [b2_voxel.cu]
 // followed by map_merge_kernel: one thread per UNIQUE scan voxel, so a voxel is
@@ -35,7 +38,10 @@ struct MapState {
     int brick = 1, cap_slots = 1, lut_stride = 16;
     unsigned capacity = 0;
     CellEntry* entries = nullptr;   // brick > 1
-    VoxEntry* vox = nullptr;        // brick == 1: dense table, centroid inside the entry
+    BrickEntry* btab = nullptr;     // brick == 1: brick hash [capacity]
+    unsigned long long* bkeys = nullptr;  // brick == 1: key of every pool brick [pool_bricks]
+    unsigned pool_bricks = 0;       // brick == 1: bricks in the pool; cent = [pool_bricks * 512] cells
+    unsigned long long max_voxels = 0;
     unsigned char* lut = nullptr;   // [capacity * lut_stride]  voxel-local id -> slot + 1
     unsigned char* lid = nullptr;   // [capacity * cap_slots]   slot -> voxel-local id
     float4* cent = nullptr;
@@ -147,103 +153,122 @@ map_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums,
     cent[pos] = cpt;
 }
 
-__global__ void vox_clear_kernel(VoxEntry* __restrict__ vox, unsigned capacity) {
+__global__ void brick_clear_kernel(BrickEntry* __restrict__ tab, unsigned capacity) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= capacity) return;
-    VoxEntry e;
+    BrickEntry e;
     e.key = kEmptyKey;
-    e.x = e.y = e.z = 0.f;
-    e.n = 0;
-    e.pad[0] = e.pad[1] = 0;
-    vox[i] = e;
+    e.index = kNoBrick;
+    e.pad = 0;
+    tab[i] = e;
 }
 
-// brick == 1: one thread per unique scan voxel; the voxel's slot is found / created with a CAS on the
-// key, everything else is exclusive to this thread.
+__device__ __forceinline__ bool brick_of_voxel(int kx, int ky, int kz, unsigned long long& bkey, unsigned& local) {
+    const int lim = (1 << 20) - 2;
+    if (kx < -lim || kx > lim || ky < -lim || ky > lim || kz < -lim || kz > lim) return false;
+    bkey = map_cell_key(kx >> 3, ky >> 3, kz >> 3);  // arithmetic shift = floor division by 8
+    local = brick_local(kx, ky, kz);
+    return true;
+}
+
+// brick == 1, pass 1: make sure the brick of every unique scan voxel exists.  The winner of the key CAS takes
+// the next pool brick and publishes its index; nobody waits for it inside this kernel (pass 2 is a separate
+// launch), so there is no spinning on another thread's progress.
 __global__ void __launch_bounds__(kBlock)
-vox_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums, const SortCtl* __restrict__ ctl,
-                 VoxEntry* __restrict__ vox, unsigned mask, double* __restrict__ acc,
-                 long long* __restrict__ counters, unsigned long long max_cells, int* __restrict__ dev_status) {
+brick_ensure_kernel(const int* __restrict__ keys3, const SortCtl* __restrict__ ctl, BrickEntry* __restrict__ tab,
+                    unsigned mask, unsigned long long* __restrict__ bkeys, unsigned pool_bricks,
+                    long long* __restrict__ counters, int* __restrict__ dev_status) {
     pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
     if (j >= ctl->nseg || *dev_status != 0) return;  // a step that already failed must not touch the map
-    const int kx = keys3[3 * j], ky = keys3[3 * j + 1], kz = keys3[3 * j + 2];
-    const int lim = (1 << 20) - 2;
-    if (kx < -lim || kx > lim || ky < -lim || ky > lim || kz < -lim || kz > lim) {
+    unsigned long long bkey;
+    unsigned local;
+    if (!brick_of_voxel(keys3[3 * j], keys3[3 * j + 1], keys3[3 * j + 2], bkey, local)) {
         atomicCAS(dev_status, 0, B2_ERR_KEY_RANGE);
         return;
     }
-    const unsigned long long ckey = map_cell_key(kx, ky, kz);
-    unsigned h = cell_hash(ckey) & mask;
-    bool fresh = false, placed = false;
+    // sorted scan voxels: the previous one is usually in the same brick and does the work
+    if (j > 0) {
+        unsigned long long pk;
+        unsigned pl;
+        if (brick_of_voxel(keys3[3 * j - 3], keys3[3 * j - 2], keys3[3 * j - 1], pk, pl) && pk == bkey) return;
+    }
+    unsigned h = cell_hash(bkey) & mask;
     for (unsigned probe = 0; probe < 4096u; ++probe) {
-        unsigned long long prev = atomicCAS(&vox[h].key, kEmptyKey, ckey);
-        if (prev == kEmptyKey) {
-            unsigned long long cells = (unsigned long long)atomicAdd((unsigned long long*)&counters[0], 1ull) + 1ull;
-            if (cells > max_cells) atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
-            atomicAdd((unsigned long long*)&counters[1], 1ull);
-            fresh = placed = true;
-            break;
+        unsigned long long cur = tab[h].key;
+        if (cur == kEmptyKey) cur = atomicCAS(&tab[h].key, kEmptyKey, bkey);
+        if (cur == kEmptyKey) {  // created here
+            const unsigned long long idx = (unsigned long long)atomicAdd((unsigned long long*)&counters[0], 1ull);
+            if (idx >= pool_bricks) {
+                atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+                return;
+            }
+            bkeys[idx] = bkey;
+            tab[h].index = (unsigned)idx;
+            return;
         }
-        if (prev == ckey) {
-            placed = true;
-            break;
-        }
+        if (cur == bkey) return;
         h = (h + 1) & mask;
     }
-    if (!placed) {
+    atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+}
+
+// brick == 1, pass 2: one thread per unique scan voxel adds its (sum, count) to the voxel's accumulator and
+// refreshes the centroid cell; a voxel is touched by exactly one thread per launch.
+__global__ void __launch_bounds__(kBlock)
+brick_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums, const SortCtl* __restrict__ ctl,
+                   const BrickEntry* __restrict__ tab, unsigned mask, float4* __restrict__ cells,
+                   double* __restrict__ acc, long long* __restrict__ counters, unsigned long long max_voxels,
+                   int* __restrict__ dev_status) {
+    pdl_enter();
+    const int j = blockIdx.x * kBlock + threadIdx.x;
+    if (j >= ctl->nseg || *dev_status != 0) return;
+    unsigned long long bkey;
+    unsigned local;
+    if (!brick_of_voxel(keys3[3 * j], keys3[3 * j + 1], keys3[3 * j + 2], bkey, local)) return;
+    const unsigned idx = brick_lookup(tab, mask, bkey);
+    if (idx == kNoBrick) {
         atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
         return;
     }
+    const size_t pos = (size_t)idx * kBrickCells + local;
     double sx = sums[4 * j], sy = sums[4 * j + 1], sz = sums[4 * j + 2], n = sums[4 * j + 3];
-    const size_t pos = h;
-    if (!fresh) {
+    const bool fresh = __float_as_int(cells[pos].w) == 0;
+    if (fresh) {
+        const unsigned long long v = (unsigned long long)atomicAdd((unsigned long long*)&counters[1], 1ull) + 1ull;
+        if (v > max_voxels) atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+    } else {
         sx = dadd(acc[4 * pos], sx);
         sy = dadd(acc[4 * pos + 1], sy);
         sz = dadd(acc[4 * pos + 2], sz);
         n = acc[4 * pos + 3] + n;
     }
     acc[4 * pos] = sx; acc[4 * pos + 1] = sy; acc[4 * pos + 2] = sz; acc[4 * pos + 3] = n;
-    vox[h].x = (float)ddiv(sx, n);
-    vox[h].y = (float)ddiv(sy, n);
-    vox[h].z = (float)ddiv(sz, n);
-    vox[h].n = (unsigned)n;
+    cells[pos] = make_float4((float)ddiv(sx, n), (float)ddiv(sy, n), (float)ddiv(sz, n), __int_as_float((int)n));
 }
 
+// Occupied voxels of the pool bricks: packed voxel key (for the canonical sort) + cell position.
 __global__ void __launch_bounds__(kBlock)
-vox_export_collect_kernel(const VoxEntry* __restrict__ vox, unsigned capacity,
-                          unsigned long long* __restrict__ out_keys, unsigned* __restrict__ out_pos,
-                          SortCtl* __restrict__ ctl, long long max_out) {
-    const unsigned h = blockIdx.x * kBlock + threadIdx.x;
-    if (h >= capacity) return;
-    const unsigned long long k = vox[h].key;
-    if (k == kEmptyKey || vox[h].n == 0) return;
+brick_export_collect_kernel(const float4* __restrict__ cells, const unsigned long long* __restrict__ bkeys,
+                            const long long* __restrict__ counters, unsigned pool_bricks,
+                            unsigned long long* __restrict__ out_keys, unsigned* __restrict__ out_pos,
+                            SortCtl* __restrict__ ctl, long long max_out) {
+    const size_t pos = (size_t)blockIdx.x * kBlock + threadIdx.x;
+    const unsigned long long used = min((unsigned long long)counters[0], (unsigned long long)pool_bricks);
+    if (pos >= used * kBrickCells) return;
+    if (__float_as_int(cells[pos].w) == 0) return;
+    const unsigned long long bk = bkeys[pos / kBrickCells];
+    const unsigned local = (unsigned)(pos % kBrickCells);
+    const unsigned long long bx = (bk >> 42) & 0x1FFFFF, by = (bk >> 21) & 0x1FFFFF, bz = bk & 0x1FFFFF;
+    // voxel coordinate + 2^20 bias = (brick coordinate + 2^20 bias) * 8 + local - 7 * 2^20
+    const long long off = 7LL << 20;
+    const unsigned long long vx = (unsigned long long)((long long)(bx * 8 + (local >> 6)) - off);
+    const unsigned long long vy = (unsigned long long)((long long)(by * 8 + ((local >> 3) & 7)) - off);
+    const unsigned long long vz = (unsigned long long)((long long)(bz * 8 + (local & 7)) - off);
     const int base = atomicAdd(&ctl->n, 1);
     if (base >= max_out) return;
-    out_keys[base] = k;  // map_cell_key of a 1-voxel cell == the packed voxel key
-    out_pos[base] = h;
-}
-
-__global__ void __launch_bounds__(kBlock)
-vox_export_write_kernel(const unsigned long long* __restrict__ keysA, const unsigned long long* __restrict__ keysB,
-                        const unsigned* __restrict__ valsA, const unsigned* __restrict__ valsB,
-                        const SortCtl* __restrict__ ctl, const VoxEntry* __restrict__ vox,
-                        const double* __restrict__ acc, float4* __restrict__ out_pts, int* __restrict__ out_keys,
-                        double* __restrict__ out_sums) {
-    const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i >= ctl->n) return;
-    const bool odd = ctl->npasses & 1;
-    const unsigned long long k = (odd ? keysB : keysA)[i];
-    const unsigned pos = (odd ? valsB : valsA)[i];
-    const VoxEntry e = vox[pos];
-    if (out_pts) out_pts[i] = make_float4(e.x, e.y, e.z, __int_as_float((int)e.n));
-    if (out_sums)
-        for (int d = 0; d < 4; ++d) out_sums[4 * (size_t)i + d] = acc[4 * (size_t)pos + d];
-    if (out_keys) {
-        out_keys[3 * i] = (int)((k >> 42) & 0x1FFFFF) - (1 << 20);
-        out_keys[3 * i + 1] = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
-        out_keys[3 * i + 2] = (int)(k & 0x1FFFFF) - (1 << 20);
-    }
+    out_keys[base] = (vx << 42) | (vy << 21) | vz;
+    out_pos[base] = (unsigned)pos;
 }
 
 // Compaction of the occupied voxels: packed 63-bit key (for the canonical sort) + slab position.
@@ -319,7 +344,7 @@ __global__ void gather_pos_kernel(const unsigned long long* keysA, const unsigne
 void map_free(Context* c) {
     MapState* m = c->map;
     if (!m) return;
-    cudaFree(m->entries); cudaFree(m->vox); cudaFree(m->lut); cudaFree(m->lid); cudaFree(m->cent); cudaFree(m->acc);
+    cudaFree(m->entries); cudaFree(m->btab); cudaFree(m->bkeys); cudaFree(m->lut); cudaFree(m->lid); cudaFree(m->cent); cudaFree(m->acc);
     cudaFree(m->counters); cudaFree(m->meta); cudaFree(m->pose); cudaFree(m->result);
     delete m;
     c->map = nullptr;
@@ -329,8 +354,10 @@ int map_reset(Context* c) {
     MapState* m = c->map;
     if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
     if (m->brick == 1) {
-        vox_clear_kernel<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->vox, m->capacity);
+        brick_clear_kernel<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->btab, m->capacity);
         B2_LAUNCH_CHECK(c);
+        // an empty cell is a zero point count; the accumulators need no clearing (a fresh cell overwrites them)
+        B2_CUDA_OK(c, cudaMemsetAsync(m->cent, 0, sizeof(float4) * (size_t)m->pool_bricks * kBrickCells, c->stream));
     } else {
         map_clear_kernel<<<div_up(m->capacity, 256), 256, 0, c->stream>>>(m->entries, m->capacity, m->cap_slots);
         B2_LAUNCH_CHECK(c);
@@ -354,6 +381,14 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
     const int cap_slots = brick * brick * brick;
     if (cap * (unsigned long long)cap_slots >= 0xFFFFFFFFull)
         return set_error(c, B2_ERR_INVALID, "map_init: capacity %llu cells x %d slots exceeds 2^32", cap, cap_slots);
+    // brick == 1: `capacity_cells` keeps its meaning as the voxel budget (B2_ERR_CAPACITY beyond 70 %); the pool
+    // gets one 8^3 brick per 64 budgeted voxels (a surface fills 60-100 of a brick's 512 cells; 24 KB per brick)
+    // and the brick hash four slots per pool brick.
+    unsigned long long pool = cap / 64;
+    if (pool < 2048) pool = 2048;
+    if (pool > (1ull << 22)) pool = 1ull << 22;
+    unsigned long long bcap = 1024;
+    while (bcap < 4 * pool) bcap <<= 1;
     // the old map goes first (its tables may be most of the memory the new one needs); the new one is only
     // published once every table exists and has been cleared, so a failed allocation leaves NO map (every
     // map call then reports B2_ERR_STATE) instead of a half-initialised one
@@ -362,19 +397,24 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
     MapState* m = new MapState();
     m->voxel = voxel; m->max_corr = max_corr; m->brick = brick; m->cap_slots = cap_slots;
     m->lut_stride = (cap_slots + 15) / 16 * 16;
-    m->capacity = (unsigned)cap;
+    m->capacity = (unsigned)(brick == 1 ? bcap : cap);
+    m->pool_bricks = brick == 1 ? (unsigned)pool : 0u;
+    m->max_voxels = (unsigned long long)(0.7 * (double)cap);
     for (int d = 0; d < 3; ++d) m->origin[d] = origin[d];
     auto alloc_all = [&]() -> cudaError_t {
         cudaError_t e;
         if (brick == 1) {
-            if ((e = cudaMalloc(&m->vox, sizeof(VoxEntry) * cap)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->btab, sizeof(BrickEntry) * bcap)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->bkeys, sizeof(unsigned long long) * pool)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->cent, sizeof(float4) * pool * kBrickCells)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->acc, sizeof(double) * 4 * pool * kBrickCells)) != cudaSuccess) return e;
         } else {
             if ((e = cudaMalloc(&m->entries, sizeof(CellEntry) * cap)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&m->lut, (size_t)cap * m->lut_stride)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&m->lid, (size_t)cap * cap_slots)) != cudaSuccess) return e;
             if ((e = cudaMalloc(&m->cent, sizeof(float4) * cap * cap_slots)) != cudaSuccess) return e;
+            if ((e = cudaMalloc(&m->acc, sizeof(double) * 4 * cap * cap_slots)) != cudaSuccess) return e;
         }
-        if ((e = cudaMalloc(&m->acc, sizeof(double) * 4 * cap * cap_slots)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&m->counters, sizeof(long long) * 2)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&m->meta, sizeof(GridMeta))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&m->pose, sizeof(double) * 16)) != cudaSuccess) return e;
@@ -401,7 +441,8 @@ int map_grid_view(Context* c, GridView* g) {
     g->pts = m->cent;
     g->meta = m->meta;
     g->is_map = m->brick == 1 ? 2 : 1;
-    g->vox = m->vox;
+    g->btab = m->btab;
+    g->pool_bricks = m->pool_bricks;
     return B2_OK;
 }
 
@@ -411,6 +452,25 @@ double map_voxel(Context* c) { return c->map ? c->map->voxel : 0.0; }
 bool map_is_empty_host(Context* c) { return !c->map || c->map->host_voxels_bound == 0; }
 void map_set_voxels_bound(Context* c, long long voxels) { if (c->map) c->map->host_voxels_bound = voxels; }
 double map_max_corr(Context* c) { return c->map ? c->map->max_corr : 0.0; }
+
+// The merge of n (upper bound; ctl->nseg live) unique voxels (keys3, sums) into the tables.
+static int merge_launch(Context* c, MapState* m, const int* keys3, const double* sums, const SortCtl* ctl, int n) {
+    if (m->brick == 1) {
+        pdl_launch(brick_ensure_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, ctl, m->btab,
+                   m->capacity - 1, m->bkeys, m->pool_bricks, m->counters, c->dev_status);
+        B2_LAUNCH_CHECK(c);
+        pdl_launch(brick_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums, ctl,
+                   (const BrickEntry*)m->btab, m->capacity - 1, m->cent, m->acc, m->counters, m->max_voxels,
+                   c->dev_status);
+    } else {
+        const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
+        pdl_launch(map_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums, ctl, m->entries,
+                   m->capacity - 1, m->lut, m->lid, m->cent, m->acc, m->counters, m->brick, m->cap_slots,
+                   m->lut_stride, max_cells, c->dev_status);
+    }
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
 
 // Fuse n_max (or *n_dev) points, transformed by T_dev (device, may be null), into the map.
 int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev) {
@@ -423,16 +483,7 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
     DownsampleOut out{dpts, dkeys, dsums, nullptr};
     VoxelSortOut vs;
     B2_TRY(voxel_downsample(c, pts, n_max, n_dev, nullptr, 1, m->voxel, /*origin_mode=*/1, m->origin, T_dev, out, &vs));
-    const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
-    if (m->brick == 1)
-        pdl_launch(vox_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
-                   (const double*)dsums, (const SortCtl*)vs.ctl, m->vox, m->capacity - 1, m->acc, m->counters,
-                   max_cells, c->dev_status);
-    else
-        pdl_launch(map_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
-                   (const double*)dsums, (const SortCtl*)vs.ctl, m->entries, m->capacity - 1, m->lut, m->lid, m->cent,
-                   m->acc, m->counters, m->brick, m->cap_slots, m->lut_stride, max_cells, c->dev_status);
-    B2_LAUNCH_CHECK(c);
+    B2_TRY(merge_launch(c, m, dkeys, dsums, vs.ctl, n_max));
     m->host_voxels_bound += n_max;
     return B2_OK;
 }
@@ -454,15 +505,7 @@ int map_merge_records(Context* c, const int* keys3, const double* sums, int n) {
     B2_WS(c, ctl, SortCtl, WS_CTL, sizeof(SortCtl));
     set_nseg_kernel<<<1, 1, 0, c->stream>>>(ctl, n);
     B2_LAUNCH_CHECK(c);
-    const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
-    if (m->brick == 1)
-        pdl_launch(vox_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums,
-                   (const SortCtl*)ctl, m->vox, m->capacity - 1, m->acc, m->counters, max_cells, c->dev_status);
-    else
-        pdl_launch(map_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums,
-                   (const SortCtl*)ctl, m->entries, m->capacity - 1, m->lut, m->lid, m->cent, m->acc, m->counters,
-                   m->brick, m->cap_slots, m->lut_stride, max_cells, c->dev_status);
-    B2_LAUNCH_CHECK(c);
+    B2_TRY(merge_launch(c, m, keys3, sums, ctl, n));
     m->host_voxels_bound += n;
     return B2_OK;
 }
@@ -495,8 +538,8 @@ int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, lon
     B2_WS(c, ctl, SortCtl, WS_CTL, sizeof(SortCtl));
     B2_CUDA_OK(c, cudaMemsetAsync(ctl, 0, sizeof(SortCtl), c->stream));
     if (m->brick == 1)
-        vox_export_collect_kernel<<<div_up(m->capacity, kBlock), kBlock, 0, c->stream>>>(m->vox, m->capacity, keysA,
-                                                                                        pos, ctl, (long long)n);
+        brick_export_collect_kernel<<<div_up((long long)m->pool_bricks * kBrickCells, kBlock), kBlock, 0, c->stream>>>(
+            m->cent, m->bkeys, m->counters, m->pool_bricks, keysA, pos, ctl, (long long)n);
     else
         map_export_collect_kernel<<<div_up(m->capacity, kBlock), kBlock, 0, c->stream>>>(
             m->entries, m->capacity, m->lid, m->brick, m->cap_slots, keysA, pos, ctl, (long long)n);
@@ -506,12 +549,8 @@ int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, lon
     B2_TRY(radix_sort_pairs(c, keysA, keysB, valsA, valsB, ctl, n, 8));
     gather_pos_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(keysA, keysB, valsA, valsB, pos, ctl);
     B2_LAUNCH_CHECK(c);
-    if (m->brick == 1)
-        vox_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->vox,
-                                                                            m->acc, out_pts, out_keys, out_sums);
-    else
-        map_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->cent,
-                                                                            m->acc, out_pts, out_keys, out_sums);
+    map_export_write_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(keysA, keysB, valsA, valsB, ctl, m->cent,
+                                                                        m->acc, out_pts, out_keys, out_sums);
     B2_LAUNCH_CHECK(c);
     B2_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return B2_OK;

@@ -42,9 +42,9 @@ MAX_CORR = 0.05
 MAX_ITER = 30
 MAP_ORIGIN = (-50.0, -50.0, -50.0)
 CORRIDOR_LEN = 210.0          # ~2.1 M voxels at 5 cm
-# hash slots of the resident map: load factor 0.06 keeps linear-probe chains (which a warp pays as the
-# maximum over its 32 lanes) short; 32 B entry + 32 B accumulator per slot = 2 GiB of the 180 GB HBM
-MAP_CAPACITY = int(os.environ.get("B2_BENCH_CAP", 1 << 25))
+# voxel budget of the resident map (B2_ERR_CAPACITY beyond 70 %): 2^23 -> a pool of 131,072 bricks of 8^3 voxels
+# (16-byte centroid cell + 32-byte fp64 accumulator per voxel: 3.1 GiB of the 180 GB HBM; ~27 k bricks are used)
+MAP_CAPACITY = int(os.environ.get("B2_BENCH_CAP", 1 << 23))
 SCAN_POINTS = 49152
 METRIC = "scans/s ICP+fuse (49k-pt scan->2M-pt map)"
 

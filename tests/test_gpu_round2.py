@@ -59,7 +59,7 @@ def test_scan_step_widens_its_sort_budget_instead_of_failing(b2):
     scans = _wide_scans(0)
     eng = b2.Engine(0)
     origin = [-100.0, -100.0, -100.0]
-    eng.map_init(0.05, origin, 0.05, 1 << 18)
+    eng.map_init(0.05, origin, 0.05, 1 << 23)  # (random points: one brick of the pool per point)
     prm = b2.make_params(0.05, 5)
     poses = []
     for s in scans + scans:              # first scan: fuse only; then eager, captured and replayed steps
@@ -78,7 +78,7 @@ def test_scan_step_widens_its_sort_budget_instead_of_failing(b2):
 def test_deferred_scan_failure_leaves_pose_and_map_untouched_and_can_be_resubmitted(b2):
     scans = _wide_scans(1)
     eng = b2.Engine(0)
-    eng.map_init(0.05, [-100.0, -100.0, -100.0], 0.05, 1 << 18)
+    eng.map_init(0.05, [-100.0, -100.0, -100.0], 0.05, 1 << 23)
     prm = b2.make_params(0.05, 5)
     pinned = [torch.from_numpy(s).pin_memory().numpy() for s in scans]
     for p in pinned:
