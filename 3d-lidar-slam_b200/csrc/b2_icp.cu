@@ -101,7 +101,7 @@ void launch_dense(Context* c, dim3 grid, const float4* src, const int* ns_dev, i
                   int* ndone, double* d2_out, int step, cudaStream_t stream, unsigned long long loop_handle) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kDenseThreads);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -260,8 +260,8 @@ int icp_grid_x(int ns_max, int n_pairs, int kind) {
     if (pairs == 1) cap = kCtasPerSm * kSMs;
     int gx;
     if (kind == 2) {
-        // dense map, single pair: one query per 4-lane group when it fits (160 groups per CTA, one CTA per SM)
-        gx = div_up(ns_max / pairs + 1, kLeaders);
+        // dense map, single pair: one query per 4-lane group when it fits (152 groups per CTA, one CTA per SM)
+        gx = div_up(ns_max / pairs + 1, kDenseLeaders);
     } else if (pairs == 1) {
         gx = div_up(ns_max, 32);  // one thread per query: spread the 32-query blocks over every SM
     } else {
@@ -448,18 +448,21 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
         fprintf(stderr, "\n");
 #ifdef B2_TAIL_TIMING
         if (dense) {
-            static unsigned long long h[64 * 148 * 8];
+            static unsigned long long h[64 * 148 * 16];
+            static unsigned mis[64];
             cudaMemcpyFromSymbol(h, g_dense_ts, sizeof(h));
-            const char* names[6] = {"entry", "waited", "folded", "solved", "searched", "exit"};
+            cudaMemcpyFromSymbol(mis, g_dense_mis, sizeof(mis));
+            const char* names[12] = {"entry", "waited", "folded", "solved", "searched", "exit", "w0:arrived", "w0:spec-issued", "w0:T-seen", "w0:cell", "w0:reloaded", "w0:finished"};
             for (int jj = 2; jj < 8 && jj < launches; ++jj) {
                 unsigned long long t0 = ~0ull;
-                for (int b = 0; b < gx; ++b) if (h[(jj * 148 + b) * 8] < t0) t0 = h[(jj * 148 + b) * 8];
+                for (int b = 0; b < gx; ++b) if (h[(jj * 148 + b) * 16] < t0) t0 = h[(jj * 148 + b) * 16];
                 unsigned long long prev_exit = 0;
-                for (int b = 0; b < gx; ++b) if (h[((jj - 1) * 148 + b) * 8 + 5] > prev_exit) prev_exit = h[((jj - 1) * 148 + b) * 8 + 5];
+                for (int b = 0; b < gx; ++b) if (h[((jj - 1) * 148 + b) * 16 + 5] > prev_exit) prev_exit = h[((jj - 1) * 148 + b) * 16 + 5];
                 fprintf(stderr, "[b2 dense launch %d] first entry %+lld ns after last exit of the previous launch |", jj, (long long)t0 - (long long)prev_exit);
-                for (int k = 0; k < 6; ++k) {
+                fprintf(stderr, " [cell changed for %u queries]", mis[jj]);
+                for (int k = 0; k < 12; ++k) {
                     unsigned long long mn = ~0ull, mx = 0, sum = 0;
-                    for (int b = 0; b < gx; ++b) { unsigned long long v = h[(jj * 148 + b) * 8 + k] - t0; if (v < mn) mn = v; if (v > mx) mx = v; sum += v; }
+                    for (int b = 0; b < gx; ++b) { unsigned long long v = h[(jj * 148 + b) * 16 + k] - t0; if (v < mn) mn = v; if (v > mx) mx = v; sum += v; }
                     fprintf(stderr, " %s %llu/%llu/%llu", names[k], mn, sum / gx, mx);
                 }
                 fprintf(stderr, "  (min/mean/max ns over CTAs)\n");
@@ -490,4 +493,15 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     return B2_OK;
 }
 
+#ifdef B2_TAIL_TIMING
+// developer builds only: the globaltimer stamps of the dense step kernel, [64 launches][148 CTAs][16 slots]
+int debug_dense_stamps(unsigned long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, g_dense_ts, sizeof(unsigned long long) * 64 * 148 * 16) == cudaSuccess ? 0 : -2;
+}
+#endif
+
 }  // namespace b2
+
+#ifdef B2_TAIL_TIMING
+extern "C" int b2_debug_dense_stamps(unsigned long long* out_host) { return b2::debug_dense_stamps(out_host); }
+#endif

@@ -4,22 +4,38 @@
 // One registration is a chain of launches of ONE kernel, and the cost of a step is its chain of dependent
 // latencies, not its bytes.  Round 1 ended a step with: CTA fold -> fence -> atomic ticket -> the LAST CTA folds
 // the 148 partials -> one thread solves -> state to global -> kernel boundary -> every CTA reloads the state
-// (13.9 us per step, half of it that tail, 147 SMs idle meanwhile).  Here the tail is gone:
+// (13.9 us per step, half of it that tail, 147 SMs idle meanwhile).  Here:
 //
-//   launch j:  every CTA loads the 148 partials of launch j-1 and the state (one memory round trip, all loads in
-//              flight together), folds them in a fixed order and evaluates the A.3 step REDUNDANTLY — same inputs,
-//              same instruction sequence, same T_j on every SM — then searches with T_j and leaves its own partial.
-//
-// No ticket, no fence, no last-CTA election, no serial section that the other SMs wait for across the chip; the
-// partials and the state ping-pong between two slots by launch parity, so a launch never overwrites what a
-// slower CTA of the same launch still has to read.  CTA 0 alone publishes the state / result records.
-// A registration of I steps is I + 2 launches: launch 0 only searches, launch I + 1 only folds and finishes.
+//   * no tail: every CTA loads the 148 partials of launch j-1 and the state, folds them in a fixed order and
+//     evaluates the A.3 step REDUNDANTLY — same inputs, same instruction sequence, same T_j on every SM.  No
+//     ticket, no fence, no last-CTA election.  Partials and state ping-pong between two slots by launch parity, so
+//     a launch never overwrites what a slower CTA of the same launch still has to read; CTA 0 alone publishes the
+//     state / result records.  A registration of I steps is I + 2 launches: launch 0 only searches, launch I + 1
+//     only folds and finishes.
+//   * the fold + solve (one thread's worth of dependent fp64, ~2.5 us) runs on a 21st CONTROL WARP while the 20
+//     search warps run the memory half of the search SPECULATIVELY with the previous transform T_{j-1}: an ICP
+//     update moves a query by far less than a 5 cm cell after the first steps, so the cell it lands in — hence
+//     the bricks and the 27 stencil cells to fetch — is almost always the one T_j will give.  The candidates
+//     wait in registers; when T_j arrives (named barrier), a query whose cell did change reloads, the others go
+//     straight to the distances.  Hash probes and cell loads are off the critical path.
+//   * distances are screened in float32 (full-rate pipes, no fp32->fp64 conversions) and only the contenders —
+//     candidates within the float32 error bound of the best — are evaluated in un-fused fp64 in the oracle's
+//     order, so correspondences, d2 and ties are bit-identical to the all-fp64 search.
 #ifdef B2_TAIL_TIMING
-__device__ unsigned long long g_dense_ts[64 * 148 * 8];
-#define B2_DTS(k) do { if (threadIdx.x == 0 && j >= 0 && j < 64) g_dense_ts[((int)j * 148 + blockIdx.x) * 8 + (k)] = gtime(); } while (0)
+__device__ unsigned long long g_dense_ts[64 * 148 * 16];
+__device__ unsigned g_dense_mis[64];
+#define B2_DTS(k) do { if ((threadIdx.x == 0 || ((k) == 2 || (k) == 3) && threadIdx.x == kDenseSearchThreads) && j >= 0 && j < 64) g_dense_ts[((int)j * 148 + blockIdx.x) * 16 + (k)] = gtime(); } while (0)
+// latest warp of the CTA to pass a point (slots 12..15)
+#define B2_DTS_MAX(k) do { if ((threadIdx.x & 31) == 0 && j >= 0 && j < 64) atomicMax(&g_dense_ts[((int)j * 148 + blockIdx.x) * 16 + (k)], gtime()); } while (0)
 #else
 #define B2_DTS(k) do {} while (0)
+#define B2_DTS_MAX(k) do {} while (0)
 #endif
+// 640 threads = 96 registers each: 19 search warps (152 four-lane groups) + the control warp (fold + solve).
+// (A 21st warp would round the CTA up to 24 warps of register allocation, i.e. 80 registers per thread.)
+constexpr int kDenseThreads = kThreads;
+constexpr int kDenseSearchThreads = kThreads - 32;
+constexpr int kDenseLeaders = kDenseSearchThreads / kGroup;  // 152 queries per CTA and round
 struct DenseState {
     IcpState st;
     long long seq;  // launches applied so far (WHILE-node bodies, whose parity is not baked in, read it first)
@@ -116,17 +132,14 @@ __device__ __noinline__ bool icp_step_local(const double* S, int ns, const IcpPa
 
 // ---- correspondence search against the brick-major map -------------------------------------------------
 // A warp serves eight queries per round, four lanes each (21.8 k queries = one round over 148 x 160 groups).
-// Round 1's search was bound by instruction issue (2.9 M warp instructions per step: every lane hashed and
-// probed its own 7 stencil cells, and the group leader alone transformed the point and accumulated the 17
-// sums while three lanes idled).  Here the work of a query is spread evenly over its four lanes:
 //   * lanes 0-2 each compute ONE axis of P = T p and of the query's cell (one IEEE division each);
-//   * the 27-cell stencil lies in at most 2 x 2 x 2 bricks: lane g looks up the two corner bricks (y, z) = (g>>1,
-//     g&1) — 2 hash probes per lane instead of 7, shared by shuffles;
-//   * cell c = g + 4k of the stencil is then a directly indexed 16-byte load (all 7 of a lane in flight at once),
-//     an emptiness test on the count in w and an un-fused fp64 distance — no key compare, no probe chain;
+//   * lane g < 3 owns the z-plane dz = g - 1 of the stencil: its 9 cells (dx, dy) have COMPILE-TIME offsets, lie in at
+//     most 2 x 2 bricks (the lane's own 1-4 hash probes, issued together), and each is a directly indexed 16-byte
+//     load, all 9 in flight at once;
 //   * arg-min over the group is a 2-step butterfly on (d2, stencil cell number): ties go to the lexicographically
 //     smallest voxel key, i.e. the lowest index of the canonical (key-ordered) export, as in the oracle;
-//   * the 17 normal-equation terms are added by all four lanes (5 / 4 / 4 / 4 terms) to the group's column.
+//   * the 17 normal-equation terms live in REGISTERS of the four lanes (5 / 4 / 4 / 4 terms) across rounds and are
+//     written to the group's shared-memory column once.
 struct DenseArgs {
     const BrickEntry* btab;
     unsigned bmask;
@@ -136,107 +149,191 @@ struct DenseArgs {
     double* d2_out;
 };
 
-__device__ __forceinline__ void dense_search_round(const DenseArgs& a, const double* __restrict__ sT,
-                                                   const double* __restrict__ sPivot, const GridMeta& meta, float4 p,
-                                                   bool valid, int q, double (*sAccL)[kLeaders], int col) {
-    const int lane = threadIdx.x & 31;
-    const int g = lane & (kGroup - 1);
-    const int lead = lane & ~(kGroup - 1);
-    // ---- P = T p and the query's cell: axis g on lane g ------------------------------------------------
-    const float pxf = __shfl_sync(kFull, p.x, lead), pyf = __shfl_sync(kFull, p.y, lead), pzf = __shfl_sync(kFull, p.z, lead);
-    valid = __shfl_sync(kFull, (int)valid, lead) != 0;
-    double Pa = 0.0;
-    int ca = 0;
-    if (g < 3) {
-        const double* row = sT + 4 * g;
-        Pa = dadd(dadd(dadd(dmul(row[0], (double)pxf), dmul(row[1], (double)pyf)), dmul(row[2], (double)pzf)), row[3]);
-        ca = voxel_coord(Pa, meta.origin[g], meta.cell);
-    }
-    const double Px = __shfl_sync(kFull, Pa, lead), Py = __shfl_sync(kFull, Pa, lead + 1), Pz = __shfl_sync(kFull, Pa, lead + 2);
-    const int cx = __shfl_sync(kFull, ca, lead), cy = __shfl_sync(kFull, ca, lead + 1), cz = __shfl_sync(kFull, ca, lead + 2);
-    const int lim = (1 << 20) - 10;
-    const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
-    const bool live = valid && in_range;  // (a query outside the key space has no neighbour)
+struct PlaneCells {   // one lane's z-plane of a query's stencil
+    float4 t[9];      // cells (dx, dy) = (k / 3 - 1, k % 3 - 1); w == 0: empty or no brick
+    unsigned pos[9];  // position in the brick pool (kNoBrick: none)
+    int cx, cy, cz;   // the query's cell they were fetched for
+};
 
-    // ---- the (up to) eight bricks under the stencil ------------------------------------------------------
-    const int bx0 = (cx - 1) >> 3, by0 = (cy - 1) >> 3, bz0 = (cz - 1) >> 3;
-    const int bx1 = (cx + 1) >> 3;
-    unsigned idx0 = kNoBrick, idx1 = kNoBrick;
+// axis g (< 3) of P = T p and of its cell; T row as four doubles
+__device__ __forceinline__ void dense_axis(const double* __restrict__ row, float4 p, double origin, double cell,
+                                           double& Pa, int& ca) {
+    Pa = dadd(dadd(dadd(dmul(row[0], (double)p.x), dmul(row[1], (double)p.y)), dmul(row[2], (double)p.z)), row[3]);
+    ca = voxel_coord(Pa, origin, cell);
+}
+
+// The same with a cell predicted by the speculative pass: [lo, hi) are the bounds of cell `cs` along this axis, a
+// nanometre inside them the IEEE division of voxel_coord cannot give anything else, so it is skipped.
+__device__ __forceinline__ void dense_axis_checked(const double* __restrict__ row, double px, double py, double pz,
+                                                   double origin, double cell, double lo, double hi, int cs,
+                                                   double& Pa, int& ca) {
+    Pa = dadd(dadd(dadd(dmul(row[0], px), dmul(row[1], py)), dmul(row[2], pz)), row[3]);
+    ca = (Pa > lo && Pa < hi) ? cs : voxel_coord(Pa, origin, cell);
+}
+
+// Fetch the nine cells of z-plane nz = cz + g - 1 around (cx, cy): four brick probes issued together, then nine
+// direct loads.  No warp-collective operation inside (callable under divergence).
+__device__ __forceinline__ void dense_load_plane(const DenseArgs& a, int cx, int cy, int cz, int g, bool live,
+                                                 PlaneCells& pc) {
+    pc.cx = cx; pc.cy = cy; pc.cz = cz;
+    const int nz = cz + g - 1;
+    const int bx0 = (cx - 1) >> 3, by0 = (cy - 1) >> 3, bzl = nz >> 3;
+    const bool xc0 = (cx >> 3) != bx0, xc1 = ((cx + 1) >> 3) != bx0;
+    const bool yc0 = (cy >> 3) != by0, yc1 = ((cy + 1) >> 3) != by0;
+    unsigned b[4] = {kNoBrick, kNoBrick, kNoBrick, kNoBrick};  // (x, y) corner bricks 00, 10, 01, 11
     if (live) {
-        const int by = (g & 2) ? (cy + 1) >> 3 : by0, bz = (g & 1) ? (cz + 1) >> 3 : bz0;
-        idx0 = brick_lookup(a.btab, a.bmask, map_cell_key(bx0, by, bz));
-        idx1 = bx1 == bx0 ? idx0 : brick_lookup(a.btab, a.bmask, map_cell_key(bx1, by, bz));
-    }
-    // ---- this lane's cells: all loads in flight before the first distance ----------------------------------
-    float4 t[kCellsPerLane];
-    bool have[kCellsPerLane];
+        const bool need[4] = {true, xc1, yc1, xc1 && yc1};
+        unsigned long long key[4];
+        unsigned h[4];
+        uint4 raw[4];
 #pragma unroll
-    for (int k = 0; k < kCellsPerLane; ++k) {
-        const int c = g + kGroup * k;
-        const int c3 = (c * 171) >> 9;  // c / 3 for c < 128
-        const int c9 = (c * 57) >> 9;   // c / 9
-        const int nx = cx + c9 - 1, ny = cy + (c3 - 3 * c9) - 1, nz = cz + (c - 3 * c3) - 1;
-        const int srcl = lead + ((((ny >> 3) != by0) ? 2 : 0) | (((nz >> 3) != bz0) ? 1 : 0));
-        const unsigned i0 = __shfl_sync(kFull, idx0, srcl), i1 = __shfl_sync(kFull, idx1, srcl);
-        const unsigned bi = (nx >> 3) != bx0 ? i1 : i0;
-        have[k] = c < 27 && bi != kNoBrick;
-        if (have[k]) t[k] = __ldg(a.cells + (size_t)bi * kBrickCells + brick_local(nx, ny, nz));
+        for (int i = 0; i < 4; ++i) {
+            key[i] = map_cell_key(bx0 + (i & 1), by0 + (i >> 1), bzl);
+            h[i] = cell_hash(key[i]) & a.bmask;
+            raw[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, kNoBrick, 0u);
+            if (need[i]) raw[i] = __ldg(reinterpret_cast<const uint4*>(a.btab + h[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned long long k = ((unsigned long long)raw[i].y << 32) | raw[i].x;
+            while (k != key[i] && k != kEmptyKey) {  // collision chain (the table is a quarter full at most)
+                h[i] = (h[i] + 1) & a.bmask;
+                raw[i] = __ldg(reinterpret_cast<const uint4*>(a.btab + h[i]));
+                k = ((unsigned long long)raw[i].y << 32) | raw[i].x;
+            }
+            b[i] = k == key[i] ? raw[i].z : kNoBrick;
+        }
+        if (!xc1) b[1] = b[0];
+        if (!yc1) b[2] = b[0];
+        if (!(xc1 && yc1)) b[3] = xc1 ? b[1] : b[2];
     }
+#pragma unroll
+    for (int ix = 0; ix < 3; ++ix) {
+        const bool xs = ix == 0 ? false : (ix == 1 ? xc0 : xc1);
+        const unsigned r0 = xs ? b[1] : b[0], r1 = xs ? b[3] : b[2];
+        const unsigned xo = ((unsigned)((cx + ix - 1) & 7) << 6) | (unsigned)(nz & 7);
+#pragma unroll
+        for (int iy = 0; iy < 3; ++iy) {
+            const bool ys = iy == 0 ? false : (iy == 1 ? yc0 : yc1);
+            const unsigned bi = ys ? r1 : r0;
+            const int k = 3 * ix + iy;
+            pc.pos[k] = bi == kNoBrick ? kNoBrick : bi * (unsigned)kBrickCells + (xo | ((unsigned)((cy + iy - 1) & 7) << 3));
+            pc.t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pc.pos[k] != kNoBrick) pc.t[k] = __ldg(a.cells + pc.pos[k]);
+        }
+    }
+}
+
+// Nearest neighbour of the group's query among the fetched cells + its contribution to the sums.
+// Warp-collective (all 32 lanes enter; `valid` is uniform over a group).
+__device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* __restrict__ sPivot, double cellw,
+                                             double Px, double Py, double Pz, const PlaneCells& pc, bool valid, int q,
+                                             double (&acc)[5]) {
+    const int g = threadIdx.x & (kGroup - 1);
+    // ---- float32 screening of this lane's nine cells: best and second-best squared distance ------------------
+    const float Pxf = (float)Px, Pyf = (float)Py, Pzf = (float)Pz;
+    float bf = INFINITY, sf = INFINITY;
+    float bx = 0.f, by = 0.f, bz = 0.f;
+    unsigned bpos = 0;
+    int bc = 0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float fx = Pxf - pc.t[k].x, fy = Pyf - pc.t[k].y, fz = Pzf - pc.t[k].z;
+        float d = fx * fx + fy * fy + fz * fz;
+        if (__float_as_int(pc.t[k].w) == 0) d = INFINITY;
+        if (d < bf) {
+            sf = bf;
+            bf = d;
+            bx = pc.t[k].x; by = pc.t[k].y; bz = pc.t[k].z;
+            bpos = pc.pos[k];
+            bc = 9 * (k / 3) + 3 * (k % 3);
+        } else if (d < sf) {
+            sf = d;
+        }
+    }
+    float gmin = bf;
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(kFull, gmin, o));
+    // ---- exact phase: let M bound |d2_f32 - d2| for every candidate (rounding of P to float32 plus the float32
+    // arithmetic).  Every candidate's d2_f32 >= d2* - M where d2* is the true minimum, so a candidate with
+    // d2_f32 > gmin + 2M has d2 > d2* and cannot be the nearest neighbour; only the contenders (normally one per
+    // group) are evaluated in fp64, in the strict order of the oracle.
     double best = INFINITY;
     int best_c = 0x7fffffff;
-    float bx = 0.f, by = 0.f, bz = 0.f;
+    unsigned best_pos = 0;
+    if (gmin < INFINITY) {
+        const float e_abs = (fmaxf(fmaxf(fabsf(Pxf), fabsf(Pyf)), fabsf(Pzf)) + 4.0f * (float)cellw + 1e-3f) * 1.2e-7f;
+        const float M = 3.5f * e_abs * sqrtf(gmin) + 3.0f * e_abs * e_abs + 1e-6f * gmin;
+        const float thr = (gmin + 2.0f * M) * 1.000002f + 1e-30f;
+        if (bf <= thr) {
+            if (sf > thr) {  // one contender in this lane
+                best = dist2_strict(Px, Py, Pz, (double)bx, (double)by, (double)bz);
+                best_c = bc + g;
+                best_pos = bpos;
+            } else {  // several within the margin (near-ties): exact pass over the lane's cells
 #pragma unroll
-    for (int k = 0; k < kCellsPerLane; ++k) {
-        if (!have[k] || __float_as_int(t[k].w) == 0) continue;
-        const double d2 = dist2_strict(Px, Py, Pz, (double)t[k].x, (double)t[k].y, (double)t[k].z);
-        if (d2 < best) {  // (cells of a lane come in increasing stencil order: ties keep the earlier one)
-            best = d2;
-            best_c = g + kGroup * k;
-            bx = t[k].x; by = t[k].y; bz = t[k].z;
+                for (int k = 0; k < 9; ++k) {
+                    if (__float_as_int(pc.t[k].w) == 0) continue;
+                    const double d2 = dist2_strict(Px, Py, Pz, (double)pc.t[k].x, (double)pc.t[k].y, (double)pc.t[k].z);
+                    if (d2 < best) {  // (increasing stencil order: ties keep the earlier cell)
+                        best = d2;
+                        best_c = 9 * (k / 3) + 3 * (k % 3) + g;
+                        best_pos = pc.pos[k];
+                        bx = pc.t[k].x; by = pc.t[k].y; bz = pc.t[k].z;
+                    }
+                }
+            }
         }
     }
     // ---- arg-min over the group: (d2, stencil cell) lexicographic ------------------------------------------
     double gbest = best;
     int gc = best_c;
+    unsigned gpos = best_pos;
 #pragma unroll
     for (int o = 1; o < kGroup; o <<= 1) {
         const double od = __shfl_xor_sync(kFull, gbest, o);
         const int oc = __shfl_xor_sync(kFull, gc, o);
+        const unsigned op = __shfl_xor_sync(kFull, gpos, o);
         if (od < gbest || (od == gbest && oc < gc)) {
             gbest = od;
             gc = oc;
+            gpos = op;
         }
     }
     const bool found = valid && gbest < a.r2;
-    const int wl = lead + (gc & (kGroup - 1));  // the lane that holds stencil cell gc (meaningful when found)
-    const float Qxf = __shfl_sync(kFull, bx, wl), Qyf = __shfl_sync(kFull, by, wl), Qzf = __shfl_sync(kFull, bz, wl);
-    if (!valid) return;
-    if (g == 0) {
-        if (a.corr_out) a.corr_out[q] = found ? gc : -1;  // (stencil cell number of the neighbour: diagnostic only)
+    if (g == 0 && valid) {
+        if (a.corr_out) a.corr_out[q] = found ? (int)gpos : -1;  // (cell position in the brick pool: diagnostic only)
         if (a.d2_out) a.d2_out[q] = found ? gbest : 0.0;
     }
+    // the neighbour's coordinates come from the lane that owns stencil cell gc (its z-plane: gc % 3)
+    const int wl = (threadIdx.x & 31 & ~(kGroup - 1)) + (found ? gc % 3 : 0);
+    float4 Q;
+    Q.x = __shfl_sync(kFull, bx, wl); Q.y = __shfl_sync(kFull, by, wl); Q.z = __shfl_sync(kFull, bz, wl);
     if (!found) return;
-    // ---- the 17 terms, spread over the four lanes (column `col` belongs to this group) ------------------------
+    // ---- the 17 terms, spread over the four lanes -----------------------------------------------------------------
     const double px = Px - sPivot[0], py = Py - sPivot[1], pz = Pz - sPivot[2];
     if (g == 0) {
-        sAccL[0][col] += px;
-        sAccL[1][col] += py;
-        sAccL[2][col] += pz;
-        sAccL[15][col] += gbest;
-        sAccL[16][col] += 1.0;
+        acc[0] += px;
+        acc[1] += py;
+        acc[2] += pz;
+        acc[3] += gbest;
+        acc[4] += 1.0;
     } else {
         const int ax = g - 1;
-        const double qa = (double)(ax == 0 ? Qxf : (ax == 1 ? Qyf : Qzf)) - sPivot[ax];
-        sAccL[3 + ax][col] += qa;
-        sAccL[6 + 3 * ax][col] += qa * px;
-        sAccL[7 + 3 * ax][col] += qa * py;
-        sAccL[8 + 3 * ax][col] += qa * pz;
+        const double qa = (double)(ax == 0 ? Q.x : (ax == 1 ? Q.y : Q.z)) - sPivot[ax];
+        acc[0] += qa;
+        acc[1] += qa * px;
+        acc[2] += qa * py;
+        acc[3] += qa * pz;
     }
 }
 
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // step >= 0: index of this launch in the chain (parity baked in by the host); step < 0: body of a CUDA-graph
 // WHILE node — the launch index is read from *seqw first (one more round trip, only in the tail of long budgets).
-__global__ void __launch_bounds__(kThreads, kCtasPerSm)
+__global__ void __launch_bounds__(kDenseThreads, 1)
 icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
                  const BrickEntry* __restrict__ btab, unsigned bmask, const float4* __restrict__ cells,
                  const GridMeta* __restrict__ metas, IcpParams prm,
@@ -244,97 +341,180 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
                  IcpResultDev* __restrict__ results, int* __restrict__ corr_out, int* __restrict__ ndone,
                  double* __restrict__ d2_out, int step, unsigned long long loop_handle) {
     constexpr int NT = 17;
+    constexpr int kParts = kDenseSearchThreads / 32;  // 20
     __shared__ DenseState sDS;
     __shared__ GridMeta sMeta;
     __shared__ double sAccL[NT][kLeaders];
-    __shared__ double sRed[kThreads / 32][kTerms];
-    __shared__ double sSum[kTerms];
-    __shared__ long long sSeq;
+    __shared__ double sRed[kParts][kTerms];
     static_assert(sizeof(DenseState) % 8 == 0 && sizeof(GridMeta) % 8 == 0, "copied as 8-byte words");
 
     long long j = step;
     B2_DTS(0);
     asm volatile("griddepcontrol.launch_dependents;");
-    if (threadIdx.x >= 32 && threadIdx.x < 32 + sizeof(GridMeta) / 8)
-        reinterpret_cast<double*>(&sMeta)[threadIdx.x - 32] = reinterpret_cast<const double*>(metas)[threadIdx.x - 32];
-    for (int i = threadIdx.x; i < NT * kLeaders; i += kThreads) (&sAccL[0][0])[i] = 0.0;
+    const bool control = threadIdx.x >= kDenseSearchThreads;
     const int lane = threadIdx.x & 31;
-    const int col = threadIdx.x / kGroup;
-    const int groups_total = gridDim.x * kLeaders;
-    const int warp_first = blockIdx.x * kLeaders + col - lane / kGroup;
+    const int g = lane & (kGroup - 1);
+    const int col = threadIdx.x / kGroup;  // (search threads)
+    const int groups_total = gridDim.x * kDenseLeaders;
+#ifdef B2_REVERSE_CTAS
+    const int q_first = (gridDim.x - 1 - blockIdx.x) * kDenseLeaders + col;
+#else
+    const int q_first = blockIdx.x * kDenseLeaders + col;  // this group's query of the first round
+#endif
+    // everything that does not depend on the previous launch: grid metadata, this group's query point
+    const GridMeta meta = *metas;
     float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-        const int q = warp_first + lane / kGroup;
-        if ((lane & (kGroup - 1)) == 0 && q < ns_max) p_first = __ldg(src + q);
-    }
+    if (!control && q_first < ns_max) p_first = __ldg(src + q_first);  // (one address per group: a broadcast load)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     B2_DTS(1);
-    if (step < 0) {
-        if (threadIdx.x == 0) sSeq = __ldcg(seqw);
-        __syncthreads();
-        j = sSeq;
-    }
+    if (step < 0) j = __ldcg(seqw);
     const int rd = (int)((j + 1) & 1), wr = (int)(j & 1);
     const int n_cta = (int)gridDim.x;
-    // one round trip: the state record and this thread's share of the partials of launch j-1
-    if (threadIdx.x < sizeof(DenseState) / 8)
-        reinterpret_cast<double*>(&sDS)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(states + rd) + threadIdx.x);
     const int ns = ns_dev ? min(__ldg(ns_dev), ns_max) : ns_max;
-    if (j > 0) {
-        grid_fold<NT>(partial + (size_t)rd * kCtasPerSm * kSMs * kTerms, n_cta, sRed, sSum);  // (two CTA barriers inside)
-    } else {
-        __syncthreads();
-    }
-    B2_DTS(2);
-    if (sDS.st.done) {  // (a finished registration turns the remaining launches into no-ops)
-        if (loop_handle && threadIdx.x == 0 && blockIdx.x == 0)
-            cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, 0u);
-        return;
-    }
-    if (threadIdx.x == 0) {
-        const bool publish = blockIdx.x == 0;
-        bool done = false;
-        if (j > 0) done = icp_step_local(sSum, ns, prm, sDS.st, results, ndone, publish);
-        sDS.seq = j + 1;
-        if (publish) {
-            states[wr] = sDS;
-            *seqw = j + 1;
-            if (loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, done ? 0u : 1u);
-        }
-    }
-    __syncthreads();
-    B2_DTS(3);
-    if (sDS.st.done) return;
-    const double* sT = sDS.st.T;
-    const double* sPivot = sDS.st.pivot;
+    const DenseState* prev = states + rd;
 
     DenseArgs a;
     a.btab = btab; a.bmask = bmask; a.cells = cells;
     a.r2 = dmul(prm.max_corr, prm.max_corr);
     a.corr_out = corr_out; a.d2_out = d2_out;
 
-    // same dealing of queries as icp_iter_kernel: 160 consecutive queries per CTA and round, the partial last
-    // round of a multi-round source in 8-query warp chunks over all CTAs
-    const int full_rounds = ns / groups_total;
-    const bool spread = full_rounds >= 1;
-    bool first = true;
-    const int q_end = spread ? full_rounds * groups_total : ns;
-    for (int q0 = warp_first; q0 < q_end; q0 += groups_total) {
-        const int q = q0 + lane / kGroup;
-        const bool valid = q < q_end;
-        float4 p = p_first;
-        if (!first && (lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
-        first = false;
-        dense_search_round(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+    if (control) {
+        // ---- control warp: state record, fold of the previous launch's partials, the A.3 step -----------------
+        if (lane < (int)(sizeof(DenseState) / 8))
+            reinterpret_cast<double*>(&sDS)[lane] = __ldcg(reinterpret_cast<const double*>(prev) + lane);
+        if (lane < kLeaders - kDenseLeaders)  // (the fold reads columns in chunks of 32: zero the padding columns)
+            for (int t = 0; t < NT; ++t) sAccL[t][kDenseLeaders + lane] = 0.0;
+        __syncwarp();
+        named_sync(1, kDenseThreads);  // the search warps have left their 20 x 17 partial sums in sRed
+        bool done = sDS.st.done != 0;
+        if (!done && j > 0) {
+            double ssum = 0.0;
+            if (lane < NT) {
+#pragma unroll
+                for (int k = 0; k < kParts; ++k) ssum += sRed[k][lane];
+            }
+            __shared__ double sSum[kTerms];
+            if (lane < NT) sSum[lane] = ssum;
+            __syncwarp();
+            B2_DTS(2);
+            if (lane == 0) done = icp_step_local(sSum, ns, prm, sDS.st, results, ndone, blockIdx.x == 0);
+        }
+        if (lane == 0) {
+            sDS.seq = j + 1;
+            if (blockIdx.x == 0) {
+                states[wr] = sDS;
+                *seqw = j + 1;
+                if (loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, sDS.st.done ? 0u : 1u);
+            }
+        }
+        __syncwarp();
+        B2_DTS(3);
+        named_sync(2, kDenseThreads);  // T_j (or `done`) is in sDS
+        if (sDS.st.done) return;
+        __syncthreads();               // (the search warps' columns are complete; the control warp has no part in the fold)
+        return;
     }
-    if (spread) {
-        const int q0 = q_end + ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * (32 / kGroup);
-        if (q0 < ns) {
-            const int q = q0 + lane / kGroup;
+
+    // ---- search warps ----------------------------------------------------------------------------------------------
+    // (a) this thread's share of the previous launch's partials: part = warp, term = lane
+    {
+        double s = 0.0;
+        if (j > 0 && lane < NT) {
+            constexpr int kMaxPer = (kCtasPerSm * kSMs + kParts - 1) / kParts;
+            const double* pp = partial + (size_t)rd * kCtasPerSm * kSMs * kTerms + lane;
+            const int part = threadIdx.x >> 5;
+            double v[kMaxPer];
+#pragma unroll
+            for (int k = 0; k < kMaxPer; ++k) {
+                const int b = part + k * kParts;
+                v[k] = b < n_cta ? __ldcg(pp + (size_t)b * kTerms) : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < kMaxPer; ++k) s += v[k];
+        }
+        // (b) meanwhile: the previous transform for the speculative fetch — ONE request per warp (the record is a
+        // single line that 148 x 19 warps read at the same moment), rows handed out by shuffles
+        const double tv = lane < 12 ? __ldg(prev->st.T + lane) : 0.0;
+        const int prev_done = __ldg(&prev->st.done);
+        double Trow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Trow[i] = __shfl_sync(kFull, tv, (4 * g + i) & 15);
+        if (lane < NT) sRed[threadIdx.x >> 5][lane] = s;
+        __threadfence_block();
+        named_arrive(1, kDenseThreads);
+        B2_DTS(6);
+        B2_DTS_MAX(14);
+
+        // (c) speculative fetch for the first round's query with T_{j-1}
+        PlaneCells pc;
+        const int warp_q0 = q_first - (lane >> 2);
+        const bool valid0 = q_first < ns;
+        const double pdx = (double)p_first.x, pdy = (double)p_first.y, pdz = (double)p_first.z;
+        double lo = 1.0, hi = 0.0;  // bounds of the predicted cell along this lane's axis (empty: nothing predicted)
+        int cs = 0;
+        {
+            double Pa = 0.0;
+            if (g < 3) {
+                dense_axis(Trow, p_first, meta.origin[g], meta.cell, Pa, cs);
+                lo = dadd(dadd(meta.origin[g], dmul((double)cs, meta.cell)), 1e-9);
+                hi = dsub(dadd(dadd(meta.origin[g], dmul((double)cs, meta.cell)), meta.cell), 1e-9);
+            }
+            const int lead = lane & ~(kGroup - 1);
+            const int cx = __shfl_sync(kFull, cs, lead), cy = __shfl_sync(kFull, cs, lead + 1), cz = __shfl_sync(kFull, cs, lead + 2);
+            const int lim = (1 << 20) - 10;
+            const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
+            dense_load_plane(a, cx, cy, cz, g, valid0 && in_range && g < 3 && !prev_done, pc);
+        }
+        B2_DTS(7);
+        {   // wait for the speculative loads here, in the shadow of the solve, not behind the barrier
+            int any = 0;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) any |= __float_as_int(pc.t[k].w);
+            asm volatile("" ::"r"(any));
+        }
+        B2_DTS_MAX(12);
+        named_sync(2, kDenseThreads);  // T_j is in sDS
+        B2_DTS(8);
+        if (sDS.st.done) return;
+        const double* sT = sDS.st.T;
+        const double* sPivot = sDS.st.pivot;
+        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        float4 pq = p_first;
+        for (int q0 = warp_q0; q0 < ns; q0 += groups_total) {  // (warp-uniform trip count: eight consecutive queries)
+            const int q = q0 + (lane >> 2);
             const bool valid = q < ns;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if ((lane & (kGroup - 1)) == 0 && valid) p = __ldg(src + q);
-            dense_search_round(a, sT, sPivot, sMeta, p, valid, q, sAccL, col);
+            if (q0 != warp_q0 && valid) pq = __ldg(src + q);
+            double Pa = 0.0;
+            int ca = 0;
+            if (g < 3) {
+                if (q0 == warp_q0) dense_axis_checked(sT + 4 * g, pdx, pdy, pdz, meta.origin[g], meta.cell, lo, hi, cs, Pa, ca);
+                else dense_axis(sT + 4 * g, pq, meta.origin[g], meta.cell, Pa, ca);
+            }
+            const int lead = lane & ~(kGroup - 1);
+            const double Px = __shfl_sync(kFull, Pa, lead), Py = __shfl_sync(kFull, Pa, lead + 1), Pz = __shfl_sync(kFull, Pa, lead + 2);
+            const int cx = __shfl_sync(kFull, ca, lead), cy = __shfl_sync(kFull, ca, lead + 1), cz = __shfl_sync(kFull, ca, lead + 2);
+            const int lim = (1 << 20) - 10;
+            const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
+            // the speculative fetch stands when the cell did not change (first round); otherwise fetch now
+            B2_DTS(9);
+#ifdef B2_TAIL_TIMING
+            if (g == 0 && valid && j >= 0 && j < 64 && (cx != pc.cx || cy != pc.cy || cz != pc.cz)) atomicAdd(&g_dense_mis[j], 1u);
+#endif
+            if (q0 != warp_q0 || cx != pc.cx || cy != pc.cy || cz != pc.cz)
+                dense_load_plane(a, cx, cy, cz, g, valid && in_range && g < 3, pc);
+            B2_DTS(10);
+            B2_DTS_MAX(13);
+            dense_finish(a, sPivot, meta.cell, Px, Py, Pz, pc, valid, q, acc);
+            B2_DTS(11);
+        }
+        // the group's column: rows by lane role
+        if (g == 0) {
+            sAccL[0][col] = acc[0]; sAccL[1][col] = acc[1]; sAccL[2][col] = acc[2];
+            sAccL[15][col] = acc[3]; sAccL[16][col] = acc[4];
+        } else {
+            const int ax = g - 1;
+            sAccL[3 + ax][col] = acc[0];
+            sAccL[6 + 3 * ax][col] = acc[1]; sAccL[7 + 3 * ax][col] = acc[2]; sAccL[8 + 3 * ax][col] = acc[3];
         }
     }
     __syncthreads();
