@@ -398,8 +398,9 @@ class Engine:
         return res
 
     def slam_scan(self, xyz_host: np.ndarray, ds_voxel: float, params: IcpParams, want_result: bool = True):
-        """xyz_host: float32 [n,3] C-contiguous host array (pinned for best H2D speed).  With
-        ``want_result=False`` the call only enqueues work (a pinned array must then stay alive until the next
+        """xyz_host: float32 [n,3] C-contiguous host array, pinned (uploaded in place) or pageable (staged
+        through the library's pinned ring).  With
+        ``want_result=False`` the call only enqueues work (a PINNED array must then stay alive until the next
         synchronising call); fetch the poses later with ``slam_results``."""
         if xyz_host.dtype != np.float32 or xyz_host.ndim != 2 or xyz_host.shape[1] != 3 or \
                 not xyz_host.flags["C_CONTIGUOUS"]:

@@ -305,6 +305,10 @@ int b2_destroy(b2_handle h) {
         cudaEventDestroy(c->ev_consumed[i]);
     }
     cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < Context::kHostStages; ++i) {
+        if (c->host_stage[i]) cudaFreeHost(c->host_stage[i]);
+        if (c->ev_host_stage[i]) cudaEventDestroy(c->ev_host_stage[i]);
+    }
     cudaFreeHost(c->result_ring);
     cudaFreeHost(c->count_ring);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ev_block[i]);
@@ -888,7 +892,36 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
         B2_WS(c, stage1, float, WS_STAGE_XYZ2, sizeof(float) * 3 * (size_t)cap);
         float* stage = sb ? stage1 : stage0;
         if (c->consumed_valid[sb]) B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[sb], 0));
-        B2_CUDA_OK(c, cudaMemcpyAsync(stage, xyz_host, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+        // A pageable source (the ordinary NumPy array a ROS callback holds) is first copied into a pinned ring
+        // slot of the library: the device copy is then truly asynchronous, overlaps the previous scan's
+        // registration, and the caller's array may be released as soon as the call returns.
+        const float* h2d_src = xyz_host;
+        cudaPointerAttributes pa;
+        const bool pageable = cudaPointerGetAttributes(&pa, xyz_host) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+        cudaGetLastError();
+        if (pageable) {
+            const size_t bytes = sizeof(float) * 3 * (size_t)n;
+            const int hs = (int)(c->host_stage_seq++ % Context::kHostStages);
+            if (c->host_stage_bytes[hs] < bytes) {
+                if (c->host_stage[hs]) {
+                    B2_CUDA_OK(c, cudaEventSynchronize(c->ev_host_stage[hs]));
+                    cudaFreeHost(c->host_stage[hs]);
+                    c->host_stage[hs] = nullptr;
+                }
+                const size_t want = sizeof(float) * 3 * (size_t)cap;
+                B2_CUDA_OK(c, cudaHostAlloc(&c->host_stage[hs], want, cudaHostAllocDefault));
+                c->host_stage_bytes[hs] = want;
+                if (!c->ev_host_stage[hs]) B2_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_host_stage[hs], cudaEventDisableTiming));
+            } else {
+                B2_CUDA_OK(c, cudaEventSynchronize(c->ev_host_stage[hs]));  // its previous upload has run
+            }
+            std::memcpy(c->host_stage[hs], xyz_host, bytes);
+            h2d_src = (const float*)c->host_stage[hs];
+            B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+            B2_CUDA_OK(c, cudaEventRecord(c->ev_host_stage[hs], c->copy_stream));
+        } else {
+            B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+        }
         B2_CUDA_OK(c, cudaEventRecord(c->ev_copied[sb], c->copy_stream));
         B2_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[sb], 0));
         pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);

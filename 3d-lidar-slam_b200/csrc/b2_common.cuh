@@ -80,6 +80,12 @@ struct Context {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool consumed_valid[2] = {false, false};
+    // pageable host scans are staged through a small ring of pinned buffers owned by the library
+    static constexpr int kHostStages = 4;
+    void* host_stage[kHostStages] = {nullptr, nullptr, nullptr, nullptr};
+    size_t host_stage_bytes[kHostStages] = {0, 0, 0, 0};
+    cudaEvent_t ev_host_stage[kHostStages] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned host_stage_seq = 0;
     // deferred read-back (b2_slam_scan with out == NULL, then b2_slam_results): pinned ring of per-scan results
     void* result_ring = nullptr;
     unsigned char* ring_first = nullptr;   // slot holds a first-scan record (pose only)

@@ -63,6 +63,30 @@ class B200ICPProcessor(ProcessPointClouds):
         super().__init__(config_path, reset_event, data_transfer,
                          logger if logger is not None else get_logger("b200 icp processor"))
 
+    # -- resuming from a resident map ------------------------------------------
+    @property
+    def engine(self):
+        """The ``_lib.Engine`` (C-ABI handle + stream) this processor drives."""
+        return self._engine
+
+    def adopt_resident_map(self) -> None:
+        """Continue from a map that is already resident in this processor's engine — filled through
+        ``engine.map_init`` + ``engine.map_fuse`` / ``map_merge_records``, e.g. the map of an earlier session or
+        the merged partial maps of a sharded replay.  The next scan is registered against it instead of becoming
+        the map ("first scan is the map", icp_processor.py:53-56, applies to an empty map only)."""
+        if self._mode != "resident":
+            raise ValueError("adopt_resident_map() needs mode='resident'")
+        self._resident_ready = True
+        self._map_cache = None
+        if self.point_clouds_in_map == 0:
+            self.point_clouds_in_map = 1
+
+    def set_pose_prior(self, T) -> None:
+        """Seed the next registration (the role of previous_transformation[-1], icp_processor.py:106)."""
+        T = np.array(T, dtype=np.float64).reshape(4, 4)
+        self._engine.set_pose(T)
+        self.previous_transformation.append(T)
+
     # -- global_map: lazy device -> host materialisation ----------------------
     @property
     def global_map(self):

@@ -177,7 +177,9 @@ int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, co
  * Runs: upload -> voxel_down_sample(ds_voxel) -> ICP against the resident map seeded with
  * the previous pose (kept on the device) -> transform + fuse the RAW scan.  When the map
  * is empty the scan is fused with the current pose and no ICP runs (icp_processor.py:53-56).
- * out may be NULL (no host read-back, fully asynchronous). */
+ * out may be NULL (no host read-back, fully asynchronous).  xyz_host may be pinned (cudaHostAlloc /
+ * cudaHostRegister: uploaded in place) or ordinary pageable memory (copied into a pinned staging ring of the
+ * library first, so the caller's buffer may be released as soon as the call returns). */
 int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
                  b2_icp_result* out);
 /* Same step for a scan that already lives on the device as float32 [n,4] rows (offline replay of
@@ -185,8 +187,8 @@ int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, con
 int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_voxel, const b2_icp_params* params,
                      b2_icp_result* out);
 /* Deferred read-back for callers that submit scans faster than they need the poses: pass out == NULL to
- * b2_slam_scan / b2_slam_scan_dev (the call then only enqueues work; a pinned host scan must stay valid
- * until the next synchronising call) and collect the results of the last `count` scans here, oldest
+ * b2_slam_scan / b2_slam_scan_dev (the call then only enqueues work; a PINNED host scan is read in place and must stay
+ * valid until the next synchronising call, a pageable one is copied before the call returns) and collect the results of the last `count` scans here, oldest
  * first (one stream synchronisation for the whole batch; at most 1024 results are kept). */
 int b2_slam_results(b2_handle h, int count, b2_icp_result* out);
 /* Number of resident-map points inside the 27-cell stencils of the transformed source points —

@@ -222,3 +222,71 @@ def radius_outlier_mask(pts, nb_points: int, radius: float) -> np.ndarray:
     lib().orc_radius_outlier_mask(_ptr(pts, C.c_double), C.c_int64(len(pts)), C.c_int(nb_points),
                                   C.c_double(radius), _ptr(keep, C.c_uint8))
     return keep.astype(bool)
+
+
+class ResidentMapCPU:
+    """The resident-map CPU leg (oracle.cpp: ResidentMap): the map stays a voxel hash of (sum, n)
+    accumulators that doubles as the search grid, nothing is re-voxelised or re-indexed per scan.
+    The C++ twin of oracle/pipeline.py:ResidentSequence (same results, bit for bit) and the
+    like-for-like CPU baseline of b2_slam_scan (icp_processor.py:43-119 with a resident index)."""
+
+    def __init__(self, map_voxel, map_origin, ds_voxel=0.02, max_corr=0.05, max_iteration=30,
+                 relative_fitness=1e-6, relative_rmse=1e-6):
+        L = lib()
+        L.orc_resident_create.restype = C.c_void_p
+        L.orc_resident_size.restype = C.c_int64
+        L.orc_resident_process.restype = C.c_int
+        org = np.ascontiguousarray(map_origin, dtype=np.float64)
+        self._h = C.c_void_p(L.orc_resident_create(C.c_double(map_voxel), _ptr(org, C.c_double), C.c_double(ds_voxel),
+                                                   C.c_double(max_corr), C.c_int(max_iteration),
+                                                   C.c_double(relative_fitness), C.c_double(relative_rmse)))
+        self.last_result = None
+
+    def close(self):
+        if self._h:
+            lib().orc_resident_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self) -> int:
+        return int(lib().orc_resident_size(self._h))
+
+    @property
+    def pose(self) -> np.ndarray:
+        T = np.zeros((4, 4))
+        lib().orc_resident_get_pose(self._h, _ptr(T, C.c_double))
+        return T
+
+    @pose.setter
+    def pose(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        lib().orc_resident_set_pose(self._h, _ptr(T, C.c_double))
+
+    def fuse(self, points, T=None):
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        T = np.eye(4) if T is None else np.ascontiguousarray(T, dtype=np.float64)
+        lib().orc_resident_fuse(self._h, _ptr(p, C.c_float), C.c_int64(len(p)), _ptr(T, C.c_double))
+
+    def process(self, points):
+        p = np.ascontiguousarray(points, dtype=np.float32)
+        T = np.zeros((4, 4))
+        fit, rmse, iters = C.c_double(0), C.c_double(0), C.c_int32(0)
+        rc = lib().orc_resident_process(self._h, _ptr(p, C.c_float), C.c_int64(len(p)), _ptr(T, C.c_double),
+                                        C.byref(fit), C.byref(rmse), C.byref(iters))
+        if rc == 1:
+            return None
+        self.last_result = ICPResult(T, fit.value, rmse.value, iters.value, None)
+        return self.last_result
+
+    def map_points(self):
+        n = self.size()
+        keys = np.zeros((n, 3), dtype=np.int32)
+        cent = np.zeros((n, 3), dtype=np.float32)
+        cnt = np.zeros(n, dtype=np.int32)
+        lib().orc_resident_export(self._h, _ptr(keys, C.c_int32), _ptr(cent, C.c_float), _ptr(cnt, C.c_int32))
+        return cent, keys, cnt

@@ -989,4 +989,235 @@ int64_t orc_radius_outlier_mask(const double* pts, int64_t n, int nb_points, dou
     return kept;
 }
 
+
+// ----------------------------------------------------------------------------
+// Resident-map CPU leg (the "resident-index CPU variant" of BASELINE.md section 2).
+// Same arithmetic as the reference sequence (A.1 down-sample, A.3/A.5 ICP, A.7
+// transform, A.1 merge at a FIXED origin) but the map is kept as per-voxel
+// (sum, n) accumulators in an open-addressing hash that doubles as the search
+// grid, so nothing is re-voxelised or re-indexed per scan: the like-for-like
+// CPU counterpart of b2_slam_scan, and the exact C++ twin of
+// oracle/pipeline.py:ResidentSequence (tests/test_oracle_kat.py compares them).
+// Nearest neighbour = exhaustive scan of the (2r+1)^3 voxel stencil,
+// r = ceil(max_corr / voxel); ties resolve to the lexicographically smallest
+// voxel key = the lowest index of the canonical (key-ordered) export that
+// orc_registration_icp would see.  Centroids are rounded to float32 as the GPU
+// stores them.  icp_processor.py:43-119 is the sequence being restated.
+// ----------------------------------------------------------------------------
+struct ResidentMap {
+    double voxel, max_corr, ds_voxel, rel_fitness, rel_rmse;
+    double origin[3];
+    int max_iteration;
+    std::vector<int64_t> tab_key;   // packed key or -1
+    std::vector<int32_t> tab_slot;
+    uint64_t mask = 0;
+    std::vector<std::array<int32_t, 3>> keys;
+    std::vector<double> acc;        // [n,4] sum x, y, z, count
+    std::vector<double> cent;       // [n,3] float32-rounded centroids, widened
+    double pose[16];
+    std::vector<double> loc;        // scan-local (sum, n) scratch, zero outside fuse()
+
+    static inline int64_t pack(int32_t x, int32_t y, int32_t z) {
+        return ((int64_t)(x & 0x1FFFFF) << 42) | ((int64_t)(y & 0x1FFFFF) << 21) | (int64_t)(z & 0x1FFFFF);
+    }
+    static inline uint64_t mix(int64_t k) {
+        uint64_t h = (uint64_t)k * 0x9E3779B97F4A7C15ull;
+        return h ^ (h >> 29);
+    }
+    void rehash(size_t want) {
+        size_t cap = 1024;
+        while (cap < want * 2) cap <<= 1;
+        tab_key.assign(cap, -1);
+        tab_slot.assign(cap, -1);
+        mask = cap - 1;
+        for (size_t s = 0; s < keys.size(); ++s) {
+            uint64_t h = mix(pack(keys[s][0], keys[s][1], keys[s][2])) & mask;
+            while (tab_key[h] != -1) h = (h + 1) & mask;
+            tab_key[h] = pack(keys[s][0], keys[s][1], keys[s][2]);
+            tab_slot[h] = (int32_t)s;
+        }
+    }
+    inline int32_t find(int32_t x, int32_t y, int32_t z) const {
+        const int64_t k = pack(x, y, z);
+        uint64_t h = mix(k) & mask;
+        while (true) {
+            const int64_t t = tab_key[h];
+            if (t == k) return tab_slot[h];
+            if (t == -1) return -1;
+            h = (h + 1) & mask;
+        }
+    }
+    int32_t find_or_add(int32_t x, int32_t y, int32_t z) {
+        if ((keys.size() + 1) * 2 > tab_key.size()) rehash((keys.size() + 1) * 2);
+        const int64_t k = pack(x, y, z);
+        uint64_t h = mix(k) & mask;
+        while (tab_key[h] != -1) {
+            if (tab_key[h] == k) return tab_slot[h];
+            h = (h + 1) & mask;
+        }
+        tab_key[h] = k;
+        tab_slot[h] = (int32_t)keys.size();
+        keys.push_back({x, y, z});
+        acc.insert(acc.end(), {0.0, 0.0, 0.0, 0.0});
+        cent.insert(cent.end(), {0.0, 0.0, 0.0});
+        return tab_slot[h];
+    }
+    // A.7 + A.1 at the map's origin: per-scan sums in input order, then one merge per touched voxel
+    void fuse(const float* pts, int64_t n, const double* T) {
+        std::vector<int32_t> slot(n);
+        std::vector<double> moved(3 * n);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            V3 r = xform(T, V3{(double)pts[3 * i], (double)pts[3 * i + 1], (double)pts[3 * i + 2]});
+            moved[3 * i] = r.x; moved[3 * i + 1] = r.y; moved[3 * i + 2] = r.z;
+        }
+        std::vector<int32_t> k3(3 * n);
+        orc_voxel_keys(moved.data(), n, voxel, origin, k3.data());
+        for (int64_t i = 0; i < n; ++i) slot[i] = find_or_add(k3[3 * i], k3[3 * i + 1], k3[3 * i + 2]);
+        // scan-local sums (input order), merged into the accumulators afterwards like the GPU's fuse
+        std::vector<int32_t> touched;
+        if (loc.size() < 4 * keys.size()) loc.resize(4 * keys.size() + 4 * 65536, 0.0);  // (kept zero between scans)
+        for (int64_t i = 0; i < n; ++i) {
+            double* a = &loc[4 * (size_t)slot[i]];
+            if (a[3] == 0.0) touched.push_back(slot[i]);
+            a[0] += moved[3 * i]; a[1] += moved[3 * i + 1]; a[2] += moved[3 * i + 2]; a[3] += 1.0;
+        }
+        for (int32_t s : touched) {
+            double* m = &acc[4 * (size_t)s];
+            double* a = &loc[4 * (size_t)s];
+            m[0] += a[0]; m[1] += a[1]; m[2] += a[2]; m[3] += a[3];
+            a[0] = a[1] = a[2] = a[3] = 0.0;
+            for (int d = 0; d < 3; ++d) cent[3 * (size_t)s + d] = (double)(float)(m[d] / m[3]);
+        }
+    }
+};
+
+void* orc_resident_create(double map_voxel, const double* origin, double ds_voxel, double max_corr,
+                          int max_iteration, double rel_fitness, double rel_rmse) {
+    ResidentMap* m = new ResidentMap();
+    m->voxel = map_voxel; m->max_corr = max_corr; m->ds_voxel = ds_voxel;
+    m->rel_fitness = rel_fitness; m->rel_rmse = rel_rmse; m->max_iteration = max_iteration;
+    std::memcpy(m->origin, origin, sizeof(m->origin));
+    mat4_identity(m->pose);
+    m->rehash(1024);
+    return m;
+}
+void orc_resident_destroy(void* h) { delete (ResidentMap*)h; }
+int64_t orc_resident_size(void* h) { return (int64_t)((ResidentMap*)h)->keys.size(); }
+void orc_resident_set_pose(void* h, const double* T) { std::memcpy(((ResidentMap*)h)->pose, T, 16 * sizeof(double)); }
+void orc_resident_get_pose(void* h, double* T) { std::memcpy(T, ((ResidentMap*)h)->pose, 16 * sizeof(double)); }
+void orc_resident_fuse(void* h, const float* pts, int64_t n, const double* T) { ((ResidentMap*)h)->fuse(pts, n, T); }
+
+// canonical (key-ordered) export: keys [n,3] int32, centroids [n,3] float32, counts [n] int32
+void orc_resident_export(void* h, int32_t* out_keys, float* out_cent, int32_t* out_counts) {
+    ResidentMap* m = (ResidentMap*)h;
+    std::vector<int32_t> order(m->keys.size());
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return m->keys[a] < m->keys[b]; });
+    for (size_t j = 0; j < order.size(); ++j) {
+        const size_t s = (size_t)order[j];
+        for (int d = 0; d < 3; ++d) {
+            if (out_keys) out_keys[3 * j + d] = m->keys[s][d];
+            if (out_cent) out_cent[3 * j + d] = (float)m->cent[3 * s + d];
+        }
+        if (out_counts) out_counts[j] = (int32_t)m->acc[4 * s + 3];
+    }
+}
+
+// One scan (float32 [n,3], sensor frame): first scan -> fuse only (returns 1); otherwise
+// down-sample (A.1, Open3D origin) -> ICP against the resident map seeded with the kept
+// pose (A.3/A.5) -> fuse the RAW scan with the new pose.  Returns 0 and fills the result.
+int orc_resident_process(void* h, const float* pts, int64_t n, double* T_out, double* fitness_out,
+                         double* rmse_out, int32_t* iters_out) {
+    ResidentMap* m = (ResidentMap*)h;
+    if (m->keys.empty()) {
+        m->fuse(pts, n, m->pose);
+        return 1;
+    }
+    std::vector<double> src(3 * n);
+    for (int64_t i = 0; i < 3 * n; ++i) src[i] = (double)pts[i];
+    int64_t ns = n;
+    if (m->ds_voxel > 0) {
+        std::vector<double> ds(3 * n);
+        ns = orc_voxel_downsample(src.data(), n, m->ds_voxel, nullptr, ds.data(), nullptr, nullptr);
+        ds.resize(3 * ns);
+        for (double& v : ds) v = (double)(float)v;  // float32 storage of the down-sampled cloud
+        src.swap(ds);
+    }
+    double T[16];
+    std::memcpy(T, m->pose, sizeof(T));
+    std::vector<double> pcd(src);
+    if (!mat4_is_identity(T)) orc_transform(src.data(), ns, T, pcd.data());
+    const int r = (int)std::ceil(m->max_corr / m->voxel - 1e-12);
+    const double r2 = m->max_corr * m->max_corr;
+    std::vector<int32_t> idx(ns), cs, ct;
+    std::vector<double> d2(ns);
+    struct Res {
+        double fitness = 0, rmse = 0;
+        int64_t n = 0;
+    };
+    auto eval = [&]() {
+        Res res;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (int64_t i = 0; i < ns; ++i) {
+            const V3 q = ld(pcd.data(), i);
+            int32_t c[3];
+            orc_voxel_keys(&pcd[3 * i], 1, m->voxel, m->origin, c);
+            double best = std::numeric_limits<double>::infinity();
+            int32_t bj = -1;
+            for (int dx = -r; dx <= r; ++dx)          // lexicographic key order: the first minimum wins ties
+                for (int dy = -r; dy <= r; ++dy)
+                    for (int dz = -r; dz <= r; ++dz) {
+                        const int32_t s = m->find(c[0] + dx, c[1] + dy, c[2] + dz);
+                        if (s < 0) continue;
+                        const double d = KDTree::dist2(&m->cent[3 * (size_t)s], q);
+                        if (d < best) {
+                            best = d;
+                            bj = s;
+                        }
+                    }
+            const bool ok = bj >= 0 && best < r2;  // strict, A.4
+            idx[i] = ok ? bj : -1;
+            d2[i] = ok ? best : 0.0;
+        }
+        cs.clear();
+        ct.clear();
+        double err2 = 0.0;
+        for (int64_t i = 0; i < ns; ++i)
+            if (idx[i] >= 0) {
+                cs.push_back((int32_t)i);
+                ct.push_back(idx[i]);
+                err2 += d2[i];
+            }
+        res.n = (int64_t)cs.size();
+        if (res.n > 0) {
+            res.fitness = (double)res.n / (double)ns;
+            res.rmse = std::sqrt(err2 / (double)res.n);
+        }
+        return res;
+    };
+    Res result = eval();
+    int it = 0;
+    for (; it < m->max_iteration; ++it) {
+        double upd[16];
+        umeyama_from_corr(pcd.data(), m->cent.data(), cs.data(), ct.data(), result.n, upd);
+        mat4_mul(upd, T, T);
+        orc_transform(pcd.data(), ns, upd, pcd.data());
+        Res backup = result;
+        result = eval();
+        if (std::fabs(backup.fitness - result.fitness) < m->rel_fitness &&
+            std::fabs(backup.rmse - result.rmse) < m->rel_rmse) {
+            ++it;
+            break;
+        }
+    }
+    std::memcpy(m->pose, T, sizeof(T));
+    if (T_out) std::memcpy(T_out, T, sizeof(T));
+    if (fitness_out) *fitness_out = result.fitness;
+    if (rmse_out) *rmse_out = result.rmse;
+    if (iters_out) *iters_out = it;
+    m->fuse(pts, n, T);
+    return 0;
+}
+
 }  // extern "C"

@@ -148,3 +148,43 @@ def test_large_batch_takes_the_sweep_driver_and_agrees_with_single_pair_runs(eng
         assert rec["fitness"][pos] == single.fitness
         assert rec["n_correspondences"][pos] == single.n_correspondences
         assert_transform_close(rec["transformation"][pos], single.matrix())
+
+
+def test_full_size_streaming_steps_match_the_resident_cpu_map(b2):
+    """The path bench.py times, end to end at full size: the ~2.1 M-voxel bench map, then consecutive 49k-pt
+    bench scans through b2_slam_scan (eager, captured and graph-replayed steps: down-sample -> dense-map ICP ->
+    fuse), against the resident CPU map of the oracle (oracle.cpp ResidentMap, the twin of
+    pipeline.ResidentSequence) fed the same samples and scans (icp_processor.py:43-119).  Iterations and
+    fitness equal, poses within 1e-4 rad / 1e-4 m, and after the sequence the two maps hold the same voxels
+    with the same point counts and centroids within 1e-5."""
+    import bench
+    from oracle import cpu as orc
+
+    eng = b2.Engine(0)
+    scene = bench.build_scene(0)
+    n_vox = bench.preload_map(eng, scene, "cuda")
+    cpu_map = orc.ResidentMapCPU(bench.MAP_VOXEL, bench.MAP_ORIGIN, ds_voxel=bench.DS_VOXEL, max_corr=bench.MAX_CORR,
+                                 max_iteration=bench.MAX_ITER)
+    for pts in bench.map_chunks(scene, "cpu"):
+        cpu_map.fuse(pts.numpy())
+    assert cpu_map.size() == n_vox
+    scans, poses = bench.make_scans(scene, 6, "cuda", seed=1)
+    prm = b2.make_params(bench.MAX_CORR, bench.MAX_ITER)
+    eng.set_pose(poses[0])
+    cpu_map.pose = poses[0]
+    for k, s in enumerate(scans):
+        res = eng.slam_scan(s, bench.DS_VOXEL, prm)
+        ores = cpu_map.process(s)
+        assert res.iterations == ores.iterations, k
+        assert res.fitness == ores.fitness, k
+        assert res.inlier_rmse == pytest.approx(ores.inlier_rmse, rel=1e-9, abs=1e-12)
+        assert_transform_close(res.matrix(), ores.transformation)
+        assert res.fitness > 0.9
+    cent, keys = eng.map_export()
+    oc, ok, on = cpu_map.map_points()
+    np.testing.assert_array_equal(keys.cpu().numpy(), ok)
+    c = cent.cpu().numpy()
+    np.testing.assert_array_equal(c[:, 3].copy().view(np.int32), on)
+    np.testing.assert_allclose(c[:, :3], oc, rtol=1e-5, atol=1e-5)
+    cpu_map.close()
+    eng.close()

@@ -291,3 +291,35 @@ def test_transform_divides_by_w():
     T[3, 3] = 2.0
     out = cpu.transform(np.array([[2.0, 4.0, 6.0]]), T)
     np.testing.assert_array_equal(out, [[1.0, 2.0, 3.0]])
+
+
+def test_resident_cpu_map_is_the_twin_of_the_resident_sequence():
+    """oracle.cpp ResidentMap (the like-for-like CPU baseline: voxel hash + stencil search, nothing rebuilt per
+    scan) must give exactly what pipeline.ResidentSequence gives by re-running registration_icp (KD-tree) on
+    the exported centroids: same iterations, bit-identical poses, fitness, rmse and map, for a map voxel equal
+    to the gate (27-cell stencil) and for the reference default 2 cm / 5 cm (7^3 stencil)."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import lidar_slam_b200  # noqa: F401  (registers the package alias)
+    from lidar_slam_b200 import synth
+    from oracle import pipeline
+
+    scene = synth.make_corridor_scene(3, length=14.0)
+    poses = synth.corridor_trajectory(scene, 4, seed=3, step=0.02)
+    scans = [synth.render_scan(scene, p, seed=300 + k).numpy()[::4].copy() for k, p in enumerate(poses)]
+    origin = np.array([-20.0, -20.0, -20.0])
+    for map_voxel in (0.05, 0.02):
+        a = pipeline.ResidentSequence(map_voxel, origin, ds_voxel=0.02, max_corr=0.05, max_iteration=30)
+        b = cpu.ResidentMapCPU(map_voxel, origin, ds_voxel=0.02, max_corr=0.05, max_iteration=30)
+        assert a.process(scans[0]) is None and b.process(scans[0]) is None  # the first scan is the map
+        for s in scans[1:]:
+            ra, rb = a.process(s), b.process(s)
+            assert ra.iterations == rb.iterations > 0
+            assert ra.fitness == rb.fitness and ra.inlier_rmse == rb.inlier_rmse
+            np.testing.assert_array_equal(ra.transformation, rb.transformation)
+        ca, ka = a.map_points()
+        cb, kb, nb = b.map_points()
+        np.testing.assert_array_equal(ka, kb)
+        np.testing.assert_array_equal(ca, cb)
+        assert nb.sum() == sum(len(s) for s in scans)
+        b.close()
