@@ -26,7 +26,7 @@ EXPORTS = [
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
     "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results", "b2_icp_batch_p2l",
-    "b2_estimate_normals_batch", "b2_map_export_records", "b2_map_merge_records",
+    "b2_estimate_normals_batch", "b2_map_export_records", "b2_map_merge_records", "b2_set_scan_path", "b2_scan_downsample",
 ]
 
 
@@ -66,6 +66,7 @@ def load():
     lib.b2_last_error.restype = C.c_char_p
     lib.b2_last_error.argtypes = [vp]
     lib.b2_set_icp_driver.argtypes = [vp, i32]
+    lib.b2_set_scan_path.argtypes = [vp, i32]
     lib.b2_launch_count.restype = C.c_ulonglong
     lib.b2_launch_count.argtypes = [vp]
     protos = {
@@ -78,6 +79,7 @@ def load():
         "b2_project_pixels": [vp, vp, i32, f64, f64, f64, f64, i32, vp],
         "b2_ingest_pointcloud2": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, pd, i32, vp, C.POINTER(C.c_int)],
         "b2_voxel_downsample": [vp, vp, i32, f64, pd, pd, vp, vp, C.POINTER(i32)],
+        "b2_scan_downsample": [vp, vp, i32, f64, vp, C.POINTER(i32)],
         "b2_estimate_normals": [vp, vp, i32, f64, i32, vp],
         "b2_nn_search": [vp, vp, i32, vp, i32, pd, f64, vp, vp],
         "b2_icp": [vp, vp, i32, vp, i32, vp, pd, C.POINTER(IcpParams), C.POINTER(IcpResult), vp],
@@ -196,6 +198,11 @@ class Engine:
         code = {"auto": 0, "group": 1, "sweep": 2, "sweep4": 3}.get(driver, driver)
         self._check(self.lib.b2_set_icp_driver(self.h, int(code)))
 
+    def set_scan_path(self, path) -> None:
+        """'hash' (default: sort-free scratch-hash passes) | 'sorted' (radix-sort pipeline) for slam_scan*."""
+        code = {"hash": 0, "sorted": 1}.get(path, path)
+        self._check(self.lib.b2_set_scan_path(self.h, int(code)))
+
     def launch_count(self) -> int:
         return int(self.lib.b2_launch_count(self.h))
 
@@ -278,6 +285,16 @@ class Engine:
         self._check(self.lib.b2_voxel_downsample(self.h, pts.data_ptr(), n, float(voxel), op, tp, out.data_ptr(),
                                                  keys.data_ptr() if want_keys else None, C.byref(m)))
         return out[:m.value], (keys[:m.value] if want_keys else None)
+
+    def scan_downsample(self, pts, voxel: float):
+        """Sort-free voxel down-sample of one scan (Open3D origin) -> centroids [m,4] (w = count bits) in the
+        order of each voxel's first input point."""
+        pts = self._pts(pts)
+        n = pts.shape[0]
+        out = self.empty_points(n)
+        m = C.c_int(0)
+        self._check(self.lib.b2_scan_downsample(self.h, pts.data_ptr(), n, float(voxel), out.data_ptr(), C.byref(m)))
+        return out[:m.value]
 
     def estimate_normals(self, pts, radius: float, max_nn: int):
         pts = self._pts(pts)

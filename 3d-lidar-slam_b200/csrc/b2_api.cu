@@ -252,6 +252,7 @@ int b2_create(int device, b2_handle* out) {
     if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return B2_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
     Context* c = new Context();
+    c->scan_path = getenv("B2_STREAM_SORTED") ? B2_SCAN_PATH_SORTED : B2_SCAN_PATH_HASH;
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
@@ -354,6 +355,17 @@ int b2_set_icp_driver(b2_handle h, int driver) {
         return set_error(c, B2_ERR_INVALID, "b2_set_icp_driver: unknown driver %d%s", driver,
                          driver == B2_ICP_DRIVER_SWEEP4 ? " (SWEEP4 is an experiment: build with B2_EXPERIMENTS=1)" : "");
     c->icp_driver = driver;
+    return B2_OK;
+}
+
+int b2_set_scan_path(b2_handle h, int path) {
+    CTX(h);
+    if (path != B2_SCAN_PATH_HASH && path != B2_SCAN_PATH_SORTED)
+        return set_error(c, B2_ERR_INVALID, "b2_set_scan_path: unknown path %d", path);
+    if (c->scan_path != path) {
+        c->scan_path = path;
+        c->ws_generation++;  // the captured scan step holds the other path's kernels
+    }
     return B2_OK;
 }
 
@@ -488,6 +500,24 @@ int b2_voxel_downsample(b2_handle h, const float* pts_dev, int n, double voxel, 
         return B2_OK;
     }
     B2_RETRY_WIDE(c, voxel_downsample_impl(c, pts_dev, n, voxel, origin, T, out_pts_dev, out_keys_dev, n_out));
+}
+
+int b2_scan_downsample(b2_handle h, const float* pts_dev, int n, double voxel, float* out_pts_dev, int* n_out) {
+    CTX(h);
+    if (n < 0 || (n > 0 && (!pts_dev || !out_pts_dev)) || !n_out) return set_error(c, B2_ERR_INVALID, "b2_scan_downsample: bad arguments");
+    if (!(voxel > 0.0)) return set_error(c, B2_ERR_INVALID, "voxel size must be > 0 (got %g)", voxel);
+    *n_out = 0;
+    if (n == 0) return B2_OK;
+    if (!stream_applicable(n))
+        return set_error(c, B2_ERR_INVALID, "b2_scan_downsample: %d points exceed the single-scan limit (use b2_voxel_downsample)", n);
+    B2_TRY(stream_begin(c, n));
+    B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
+    B2_TRY(stream_downsample(c, (const float4*)pts_dev, n, nullptr, voxel, (float4*)out_pts_dev, cnt));
+    int* hn = (int*)c->host_mailbox;
+    B2_CUDA_OK(c, cudaMemcpyAsync(hn, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    *n_out = *hn;
+    return B2_OK;
 }
 
 int b2_estimate_normals(b2_handle h, const float* pts_dev, int n, double radius, int max_nn, float* out_normals_dev) {
@@ -774,17 +804,24 @@ static int slam_body(Context* c, const float4* scan, int n, const int* n_dev, do
     // n is the capacity the kernels are launched for; the live point count sits in *n_dev
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
+    // one scan needs no sort: scratch-hash passes (b2_stream.cu) unless b2_set_scan_path selected the radix path
+    const bool fast = c->scan_path == B2_SCAN_PATH_HASH && stream_applicable(n);
+    if (fast) B2_TRY(stream_begin(c, n));
     if (!map_empty) {
         const float4* src = scan;
         const int* ns_dev = n_dev;
         if (ds_voxel > 0.0) {
             B2_WS(c, sdown, float4, WS_SRC_DOWN, sizeof(float4) * (size_t)n);
-            DownsampleOut dso{sdown, nullptr, nullptr, nullptr};
-            VoxelSortOut vs;
-            B2_TRY(voxel_downsample(c, scan, n, n_dev, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
-            // keep the voxel count where later sorts cannot overwrite it
             B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
-            B2_CUDA_OK(c, cudaMemcpyAsync(cnt, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            if (fast) {
+                B2_TRY(stream_downsample(c, scan, n, n_dev, ds_voxel, sdown, cnt));
+            } else {
+                DownsampleOut dso{sdown, nullptr, nullptr, nullptr};
+                VoxelSortOut vs;
+                B2_TRY(voxel_downsample(c, scan, n, n_dev, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
+                // keep the voxel count where later sorts cannot overwrite it
+                B2_CUDA_OK(c, cudaMemcpyAsync(cnt, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+            }
             src = sdown;
             ns_dev = cnt;
         }
@@ -793,12 +830,14 @@ static int slam_body(Context* c, const float4* scan, int n, const int* n_dev, do
         B2_TRY(icp_run(c, src, n, nullptr, ns_dev, 1, g, nullptr, nullptr, pose, to_internal(params), res, nullptr,
                        nullptr, 0, 0));
         // fuse with the registered pose straight from the result record; the pose prior is committed last
-        B2_TRY(map_fuse(c, scan, n, n_dev, res->T));
+        if (fast) B2_TRY(map_fuse_stream(c, scan, n, n_dev, res->T));
+        else B2_TRY(map_fuse(c, scan, n, n_dev, res->T));
         copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose, c->dev_status);
         B2_LAUNCH_CHECK(c);
         return B2_OK;
     }
-    B2_TRY(map_fuse(c, scan, n, n_dev, pose));
+    if (fast) B2_TRY(map_fuse_stream(c, scan, n, n_dev, pose));
+    else B2_TRY(map_fuse(c, scan, n, n_dev, pose));
     return B2_OK;
 }
 

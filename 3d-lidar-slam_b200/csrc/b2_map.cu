@@ -488,6 +488,19 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
     return B2_OK;
 }
 
+int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev) {
+    MapState* m = c->map;
+    if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
+    if (n_max <= 0) return B2_OK;
+    B2_WS(c, dkeys, int, WS_TMP_KEYS, sizeof(int) * 3 * (size_t)n_max);
+    B2_WS(c, dsums, double, WS_SUMS, sizeof(double) * 4 * (size_t)n_max);
+    SortCtl* ctl = nullptr;
+    B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl));
+    B2_TRY(merge_launch(c, m, dkeys, dsums, ctl, n_max));
+    m->host_voxels_bound += n_max;
+    return B2_OK;
+}
+
 namespace {
 __global__ void set_nseg_kernel(SortCtl* ctl, int n) {
     ctl->n = n;

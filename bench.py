@@ -61,7 +61,7 @@ SCENE_SEED = 1000
 START_X = 20.0
 METRIC = "scans/s ICP+fuse (49k-pt scan->2M-pt map)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, `ncu --set full`
-# (profiles/r02_icp_dense_full_raw.csv; cold caches between replays)
+# (profiles/r02/icp_dense_2M_full_raw.csv; cold caches between replays)
 ICP_DENSE_TRAFFIC = int(os.environ.get("B2_BENCH_TRAFFIC", 0)) or None
 
 
@@ -422,7 +422,7 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
 
 
 # traffic of the dense kernel from the committed ncu capture (bytes per launch); see profiles/README.md
-ICP_DENSE_TRAFFIC_DEFAULT = 1_930_000
+ICP_DENSE_TRAFFIC_DEFAULT = 781_000
 
 
 def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2batch):

@@ -76,6 +76,15 @@ unsigned long long b2_launch_count(b2_handle h);
 #define B2_ICP_DRIVER_SWEEP 2
 #define B2_ICP_DRIVER_SWEEP4 3 /* experiment (measured slower), only in B2_EXPERIMENTS=1 builds: four lanes per query */
 int b2_set_icp_driver(b2_handle h, int driver);
+/* How b2_slam_scan / b2_slam_scan_dev voxelise a scan (both the 2 cm down-sample in front of ICP and the
+ * fusion into the map; voxel keys, occupancy and counts are identical, centroids agree to ~1e-15 relative):
+ * B2_SCAN_PATH_HASH (default) = one scratch hash per scan filled with atomics, no sort (b2_stream.cu: 8 launches);
+ * B2_SCAN_PATH_SORTED = the radix-sort pipeline of b2_voxel_downsample (28 launches; in-order fp64 sums, the
+ * down-sampled source comes out in voxel-key order).  The environment variable B2_STREAM_SORTED=1 selects
+ * SORTED at b2_create. */
+#define B2_SCAN_PATH_HASH 0
+#define B2_SCAN_PATH_SORTED 1
+int b2_set_scan_path(b2_handle h, int path);
 
 /* ---- layout helpers ----------------------------------------------------- */
 /* float32 [n,3] (host when src_on_host != 0, else device) -> float32 [n,4] device rows.
@@ -108,6 +117,10 @@ int b2_ingest_pointcloud2(b2_handle h, const void* data, int data_on_host, int n
  * count of the voxel), out_keys_dev int32 [n,3] or NULL, *n_out = voxel count. */
 int b2_voxel_downsample(b2_handle h, const float* pts_dev, int n, double voxel, const double* origin,
                         const double* T, float* out_pts_dev, int* out_keys_dev, int* n_out);
+/* The same down-sample for ONE scan (n <= 151,552 points) without a sort — the pass b2_slam_scan runs in front
+ * of ICP (icp_processor.py:90): Open3D's origin, centroids bit-identical to b2_voxel_downsample's, emitted in the
+ * order of each voxel's first point in the input (pixel order) instead of voxel-key order. */
+int b2_scan_downsample(b2_handle h, const float* pts_dev, int n, double voxel, float* out_pts_dev, int* n_out);
 
 /* PointCloud.estimate_normals(KDTreeSearchParamHybrid(radius, max_nn))
  * (icp_processor.py:94-99).  out_normals_dev float32 [n,4] (w = 0).

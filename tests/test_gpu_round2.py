@@ -60,6 +60,7 @@ def test_scan_step_widens_its_sort_budget_instead_of_failing(b2):
     eng = b2.Engine(0)
     origin = [-100.0, -100.0, -100.0]
     eng.map_init(0.05, origin, 0.05, 1 << 23)  # (random points: one brick of the pool per point)
+    eng.set_scan_path("sorted")          # (the default scratch-hash passes have no sort budget to exceed)
     prm = b2.make_params(0.05, 5)
     poses = []
     for s in scans + scans:              # first scan: fuse only; then eager, captured and replayed steps
@@ -79,6 +80,7 @@ def test_deferred_scan_failure_leaves_pose_and_map_untouched_and_can_be_resubmit
     scans = _wide_scans(1)
     eng = b2.Engine(0)
     eng.map_init(0.05, [-100.0, -100.0, -100.0], 0.05, 1 << 23)
+    eng.set_scan_path("sorted")
     prm = b2.make_params(0.05, 5)
     pinned = [torch.from_numpy(s).pin_memory().numpy() for s in scans]
     for p in pinned:
@@ -146,3 +148,65 @@ def test_partial_maps_merge_to_the_voxel_downsample_of_the_concatenation(b2):
     _, s2 = merged.map_export_records()
     assert float(s2[:, 3].sum().item()) == float(on.sum()) + float(s0[:, 3].sum().item())
     merged.close()
+
+
+def _rows_sorted(a):
+    a = np.ascontiguousarray(a)
+    return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def test_scan_downsample_without_a_sort_is_bit_identical_to_the_oracle(engine):
+    """b2_scan_downsample (scratch hash + fp64 atomics, what b2_slam_scan runs in front of ICP,
+    icp_processor.py:90): the sum of the float32 coordinates of one voxel is exact in fp64, so the centroids
+    and counts equal the oracle's in-order sums bit for bit; rows come in order of first appearance."""
+    from lidar_slam_b200 import synth
+
+    for seed, keep in ((0, 1.0), (1, 0.6)):
+        scene = synth.make_corridor_scene(seed, length=14.0)
+        pose = synth.corridor_trajectory(scene, 1, seed=seed)[0]
+        scan = synth.project_records(synth.scan_records(synth.render_depth(scene, pose, seed=seed), keep_prob=keep,
+                                                        seed=seed)).numpy()
+        got = engine.scan_downsample(engine.pack(scan), 0.02).cpu().numpy()
+        oc, ok, on = orc.voxel_downsample(f64(scan), 0.02)
+        assert len(got) == len(oc)
+        want = np.concatenate([oc.astype(np.float32), on.view(np.float32)[:, None]], axis=1)
+        np.testing.assert_array_equal(_rows_sorted(got).view(np.int32), _rows_sorted(want).view(np.int32))
+        # order of first appearance: the voxel of input point 0 comes first, and the row order follows the
+        # first input index of every voxel
+        keys = orc.voxel_keys(f64(scan), 0.02)
+        first = {}
+        for i, k in enumerate(map(tuple, keys.tolist())):
+            first.setdefault(k, i)
+        order = sorted(first, key=first.get)
+        pos = {tuple(k): j for j, k in enumerate(ok.tolist())}
+        want_rows = want[[pos[k] for k in order]]
+        np.testing.assert_array_equal(got.view(np.int32), want_rows.view(np.int32))
+
+
+def test_hash_and_sorted_scan_paths_register_and_fuse_alike(b2):
+    """The sort-free scan step against the radix-sort scan step on the same sequence (eager, captured and
+    replayed steps): same iterations and fitness, poses within 1e-7 (the source order differs, hence the summation order), the same voxels with the same point counts
+    in the map, centroids within 1e-6 relative (per-scan sums: fixed point vs in-order fp64)."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(11, length=14.0)
+    poses = synth.corridor_trajectory(scene, 8, seed=11, step=0.02)
+    scans = [synth.render_scan(scene, p, seed=900 + k).numpy() for k, p in enumerate(poses)]
+    out = {}
+    for path in ("hash", "sorted"):
+        eng = b2.Engine(0)
+        eng.map_init(0.05, [-20.0, -20.0, -20.0], 0.05, 1 << 19)
+        eng.set_scan_path(path)
+        res = [eng.slam_scan(s, 0.02, b2.make_params(0.05, 30)) for s in scans]
+        cent, keys = eng.map_export()
+        out[path] = (res, cent.cpu().numpy().copy(), keys.cpu().numpy().copy(), eng.launch_count())
+        eng.close()
+    (ra, ca, ka, la), (rb, cb, kb, lb) = out["hash"], out["sorted"]
+    assert la < lb - 100                 # really a different, shorter pipeline
+    for k in range(1, len(scans)):
+        assert ra[k].iterations == rb[k].iterations > 0, k
+        assert ra[k].fitness == rb[k].fitness, k
+        np.testing.assert_allclose(ra[k].matrix(), rb[k].matrix(), rtol=0, atol=1e-7)
+    np.testing.assert_array_equal(ka, kb)
+    np.testing.assert_array_equal(ca[:, 3].copy().view(np.int32), cb[:, 3].copy().view(np.int32))
+    np.testing.assert_allclose(ca[:, :3], cb[:, :3], rtol=1e-6, atol=1e-6)
