@@ -31,11 +31,18 @@ __device__ unsigned g_dense_mis[64];
 #define B2_DTS(k) do {} while (0)
 #define B2_DTS_MAX(k) do {} while (0)
 #endif
-// 640 threads = 96 registers each: 19 search warps (152 four-lane groups) + the control warp (fold + solve).
-// (A 21st warp would round the CTA up to 24 warps of register allocation, i.e. 80 registers per thread.)
+// 640 threads = 96 registers each: 19 search warps + the control warp (fold + solve).  (A 21st warp would put
+// six warps on one SM sub-partition: 6 x 32 x 96 registers > its 16,384.)  A query is served by THREE lanes (one
+// z-plane of the stencil each), ten queries per warp, lanes 30 and 31 idle: 190 queries per CTA and round, i.e.
+// 28,120 per round over 148 SMs.  With four lanes per query (152 per CTA, 22,496 per round) a quarter of the
+// bench scans (21-24 k points after the 2 cm down-sample) overflowed into a second round on the first CTAs — a
+// second, unspeculated round trip to the map on the critical path of every step of those scans (+3 us).
 constexpr int kDenseThreads = kThreads;
 constexpr int kDenseSearchThreads = kThreads - 32;
-constexpr int kDenseLeaders = kDenseSearchThreads / kGroup;  // 152 queries per CTA and round
+constexpr int kDenseLanes = 3;                                   // lanes per query
+constexpr int kDenseQueriesPerWarp = 10;
+constexpr int kDenseLeaders = (kDenseSearchThreads / 32) * kDenseQueriesPerWarp;  // 190 queries per CTA and round
+constexpr int kDenseCols = 192;                                  // accumulator columns (padded to whole warps)
 struct DenseState {
     IcpState st;
     long long seq;  // launches applied so far (WHILE-node bodies, whose parity is not baked in, read it first)
@@ -131,14 +138,15 @@ __device__ __noinline__ bool icp_step_local(const double* S, int ns, const IcpPa
 }
 
 // ---- correspondence search against the brick-major map -------------------------------------------------
-// A warp serves eight queries per round, four lanes each (21.8 k queries = one round over 148 x 160 groups).
-//   * lanes 0-2 each compute ONE axis of P = T p and of the query's cell (one IEEE division each);
-//   * lane g < 3 owns the z-plane dz = g - 1 of the stencil: its 9 cells (dx, dy) have COMPILE-TIME offsets, lie in at
+// A warp serves ten queries per round, three lanes each (lanes 30 / 31 idle):
+//   * lane g computes axis g of P = T p and of the query's cell (one IEEE division each);
+//   * lane g owns the z-plane dz = g - 1 of the stencil: its 9 cells (dx, dy) have COMPILE-TIME offsets, lie in at
 //     most 2 x 2 bricks (the lane's own 1-4 hash probes, issued together), and each is a directly indexed 16-byte
 //     load, all 9 in flight at once;
-//   * arg-min over the group is a 2-step butterfly on (d2, stencil cell number): ties go to the lexicographically
-//     smallest voxel key, i.e. the lowest index of the canonical (key-ordered) export, as in the oracle;
-//   * the 17 normal-equation terms live in REGISTERS of the four lanes (5 / 4 / 4 / 4 terms) across rounds and are
+//   * arg-min over the group: every lane reads the three lanes' (d2, stencil cell number) and keeps the
+//     lexicographic minimum: ties go to the smallest voxel key, i.e. the lowest index of the canonical (key-ordered)
+//     export, as in the oracle;
+//   * the 17 normal-equation terms live in REGISTERS of the three lanes (6 / 6 / 5 terms) across rounds and are
 //     written to the group's shared-memory column once.
 struct DenseArgs {
     const BrickEntry* btab;
@@ -225,11 +233,11 @@ __device__ __forceinline__ void dense_load_plane(const DenseArgs& a, int cx, int
 }
 
 // Nearest neighbour of the group's query among the fetched cells + its contribution to the sums.
-// Warp-collective (all 32 lanes enter; `valid` is uniform over a group).
+// Warp-collective (all 32 lanes enter; `valid` is uniform over a group; g = lane's z-plane 0..2, lead = the
+// group's first lane; lanes 30 / 31 come in with g >= 3, valid == false and empty cells).
 __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* __restrict__ sPivot, double cellw,
                                              double Px, double Py, double Pz, const PlaneCells& pc, bool valid, int q,
-                                             double (&acc)[5]) {
-    const int g = threadIdx.x & (kGroup - 1);
+                                             int g, int lead, double (&acc)[6]) {
     // ---- float32 screening of this lane's nine cells: best and second-best squared distance ------------------
     const float Pxf = (float)Px, Pyf = (float)Py, Pzf = (float)Pz;
     float bf = INFINITY, sf = INFINITY;
@@ -251,9 +259,8 @@ __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* _
             sf = d;
         }
     }
-    float gmin = bf;
-#pragma unroll
-    for (int o = 1; o < kGroup; o <<= 1) gmin = fminf(gmin, __shfl_xor_sync(kFull, gmin, o));
+    const float gmin = fminf(fminf(__shfl_sync(kFull, bf, lead), __shfl_sync(kFull, bf, lead + 1)),
+                             __shfl_sync(kFull, bf, lead + 2));
     // ---- exact phase: let M bound |d2_f32 - d2| for every candidate (rounding of P to float32 plus the float32
     // arithmetic).  Every candidate's d2_f32 >= d2* - M where d2* is the true minimum, so a candidate with
     // d2_f32 > gmin + 2M has d2 > d2* and cannot be the nearest neighbour; only the contenders (normally one per
@@ -286,18 +293,32 @@ __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* _
         }
     }
     // ---- arg-min over the group: (d2, stencil cell) lexicographic ------------------------------------------
-    double gbest = best;
-    int gc = best_c;
-    unsigned gpos = best_pos;
+    // Normally exactly one lane of the group holds a contender: its values are the group's (one ballot, no
+    // comparison of doubles across lanes); otherwise (near-ties across z-planes, or no candidate at all) every
+    // lane reads the three lanes' (d2, cell) and keeps the lexicographic minimum.
+    const unsigned has = (__ballot_sync(kFull, best < INFINITY) >> lead) & 7u;
+    double gbest;
+    int gc;
+    unsigned gpos;
+    if (__all_sync(kFull, __popc(has) == 1)) {  // (warp-uniform: the shuffles below name all 32 lanes)
+        const int wlane = lead + (__ffs(has) - 1);
+        gbest = __shfl_sync(kFull, best, wlane);
+        gc = __shfl_sync(kFull, best_c, wlane);
+        gpos = __shfl_sync(kFull, best_pos, wlane);
+    } else {
+        gbest = __shfl_sync(kFull, best, lead);
+        gc = __shfl_sync(kFull, best_c, lead);
+        gpos = __shfl_sync(kFull, best_pos, lead);
 #pragma unroll
-    for (int o = 1; o < kGroup; o <<= 1) {
-        const double od = __shfl_xor_sync(kFull, gbest, o);
-        const int oc = __shfl_xor_sync(kFull, gc, o);
-        const unsigned op = __shfl_xor_sync(kFull, gpos, o);
-        if (od < gbest || (od == gbest && oc < gc)) {
-            gbest = od;
-            gc = oc;
-            gpos = op;
+        for (int o = 1; o < kDenseLanes; ++o) {
+            const double od = __shfl_sync(kFull, best, lead + o);
+            const int oc = __shfl_sync(kFull, best_c, lead + o);
+            const unsigned op = __shfl_sync(kFull, best_pos, lead + o);
+            if (od < gbest || (od == gbest && oc < gc)) {
+                gbest = od;
+                gc = oc;
+                gpos = op;
+            }
         }
     }
     const bool found = valid && gbest < a.r2;
@@ -306,26 +327,20 @@ __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* _
         if (a.d2_out) a.d2_out[q] = found ? gbest : 0.0;
     }
     // the neighbour's coordinates come from the lane that owns stencil cell gc (its z-plane: gc % 3)
-    const int wl = (threadIdx.x & 31 & ~(kGroup - 1)) + (found ? gc % 3 : 0);
+    const int wl = lead + (found ? gc % 3 : 0);
     float4 Q;
     Q.x = __shfl_sync(kFull, bx, wl); Q.y = __shfl_sync(kFull, by, wl); Q.z = __shfl_sync(kFull, bz, wl);
-    if (!found) return;
-    // ---- the 17 terms, spread over the four lanes -----------------------------------------------------------------
+    if (!found || g >= kDenseLanes) return;
+    // ---- the 17 terms, spread over the three lanes: lane g holds axis g of q (q_g, q_g p^T) and p_g; lane 0 also
+    // the squared distance, lane 1 the count ----------------------------------------------------------------------
     const double px = Px - sPivot[0], py = Py - sPivot[1], pz = Pz - sPivot[2];
-    if (g == 0) {
-        acc[0] += px;
-        acc[1] += py;
-        acc[2] += pz;
-        acc[3] += gbest;
-        acc[4] += 1.0;
-    } else {
-        const int ax = g - 1;
-        const double qa = (double)(ax == 0 ? Q.x : (ax == 1 ? Q.y : Q.z)) - sPivot[ax];
-        acc[0] += qa;
-        acc[1] += qa * px;
-        acc[2] += qa * py;
-        acc[3] += qa * pz;
-    }
+    const double qa = (double)(g == 0 ? Q.x : (g == 1 ? Q.y : Q.z)) - sPivot[g];
+    acc[0] += qa;
+    acc[1] += qa * px;
+    acc[2] += qa * py;
+    acc[3] += qa * pz;
+    acc[4] += g == 0 ? px : (g == 1 ? py : pz);
+    acc[5] += g == 0 ? gbest : (g == 1 ? 1.0 : 0.0);
 }
 
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -344,7 +359,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     constexpr int kParts = kDenseSearchThreads / 32;  // 20
     __shared__ DenseState sDS;
     __shared__ GridMeta sMeta;
-    __shared__ double sAccL[NT][kLeaders];
+    __shared__ double sAccL[NT][kDenseCols];
     __shared__ double sRed[kParts][kTerms];
     static_assert(sizeof(DenseState) % 8 == 0 && sizeof(GridMeta) % 8 == 0, "copied as 8-byte words");
 
@@ -353,24 +368,29 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     asm volatile("griddepcontrol.launch_dependents;");
     const bool control = threadIdx.x >= kDenseSearchThreads;
     const int lane = threadIdx.x & 31;
-    const int g = lane & (kGroup - 1);
-    const int col = threadIdx.x / kGroup;  // (search threads)
-    const int groups_total = gridDim.x * kDenseLeaders;
-#ifdef B2_REVERSE_CTAS
-    const int q_first = (gridDim.x - 1 - blockIdx.x) * kDenseLeaders + col;
-#else
-    const int q_first = blockIdx.x * kDenseLeaders + col;  // this group's query of the first round
-#endif
+    const int grp = min(lane / kDenseLanes, kDenseQueriesPerWarp - 1);  // (lanes 30, 31: g = 3, 4 -> idle)
+    const int g = lane - kDenseLanes * grp;
+    const int lead = kDenseLanes * grp;
+    const int col = (threadIdx.x >> 5) * kDenseQueriesPerWarp + grp;  // (search threads)
+    // The source size is final before the first launch of the chain starts (the init kernel ahead of it completes
+    // first), so it can be read ahead of the grid dependency.  The queries are dealt evenly: every CTA takes
+    // ceil(ns / CTAs) of them, in whole warps of ten (148 each for a 21.8 k-point source: 15 of the 19 search warps),
+    // and only a source beyond 190 per CTA makes a second round.
+    const int n_cta = (int)gridDim.x;
+    const int ns = ns_dev ? min(__ldcg(ns_dev), ns_max) : ns_max;
+    const int share = min(kDenseLeaders, ((ns + n_cta - 1) / n_cta + kDenseQueriesPerWarp - 1) / kDenseQueriesPerWarp *
+                                             kDenseQueriesPerWarp);
+    const int groups_total = n_cta * share;
+    const bool has_query = col < share && g < kDenseLanes;
+    const int q_first = blockIdx.x * share + col;  // this group's query of the first round
     // everything that does not depend on the previous launch: grid metadata, this group's query point
     const GridMeta meta = *metas;
     float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (!control && q_first < ns_max) p_first = __ldg(src + q_first);  // (one address per group: a broadcast load)
+    if (!control && has_query && q_first < ns) p_first = __ldg(src + q_first);  // (one address per group)
     asm volatile("griddepcontrol.wait;" ::: "memory");
     B2_DTS(1);
     if (step < 0) j = __ldcg(seqw);
     const int rd = (int)((j + 1) & 1), wr = (int)(j & 1);
-    const int n_cta = (int)gridDim.x;
-    const int ns = ns_dev ? min(__ldg(ns_dev), ns_max) : ns_max;
     const DenseState* prev = states + rd;
 
     DenseArgs a;
@@ -382,7 +402,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         // ---- control warp: state record, fold of the previous launch's partials, the A.3 step -----------------
         if (lane < (int)(sizeof(DenseState) / 8))
             reinterpret_cast<double*>(&sDS)[lane] = __ldcg(reinterpret_cast<const double*>(prev) + lane);
-        if (lane < kLeaders - kDenseLeaders)  // (the fold reads columns in chunks of 32: zero the padding columns)
+        if (lane < kDenseCols - kDenseLeaders)  // (the fold reads columns in chunks of 32: zero the padding columns)
             for (int t = 0; t < NT; ++t) sAccL[t][kDenseLeaders + lane] = 0.0;
         __syncwarp();
         named_sync(1, kDenseThreads);  // the search warps have left their 20 x 17 partial sums in sRed
@@ -447,8 +467,8 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
 
         // (c) speculative fetch for the first round's query with T_{j-1}
         PlaneCells pc;
-        const int warp_q0 = q_first - (lane >> 2);
-        const bool valid0 = q_first < ns;
+        const int warp_q0 = q_first - grp;
+        const bool valid0 = q_first < ns && has_query;
         const double pdx = (double)p_first.x, pdy = (double)p_first.y, pdz = (double)p_first.z;
         double lo = 1.0, hi = 0.0;  // bounds of the predicted cell along this lane's axis (empty: nothing predicted)
         int cs = 0;
@@ -459,11 +479,10 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
                 lo = dadd(dadd(meta.origin[g], dmul((double)cs, meta.cell)), 1e-9);
                 hi = dsub(dadd(dadd(meta.origin[g], dmul((double)cs, meta.cell)), meta.cell), 1e-9);
             }
-            const int lead = lane & ~(kGroup - 1);
             const int cx = __shfl_sync(kFull, cs, lead), cy = __shfl_sync(kFull, cs, lead + 1), cz = __shfl_sync(kFull, cs, lead + 2);
             const int lim = (1 << 20) - 10;
             const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
-            dense_load_plane(a, cx, cy, cz, g, valid0 && in_range && g < 3 && !prev_done, pc);
+            dense_load_plane(a, cx, cy, cz, g, valid0 && in_range && !prev_done, pc);
         }
         B2_DTS(7);
         {   // wait for the speculative loads here, in the shadow of the solve, not behind the barrier
@@ -478,11 +497,12 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         if (sDS.st.done) return;
         const double* sT = sDS.st.T;
         const double* sPivot = sDS.st.pivot;
-        double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         float4 pq = p_first;
-        for (int q0 = warp_q0; q0 < ns; q0 += groups_total) {  // (warp-uniform trip count: eight consecutive queries)
-            const int q = q0 + (lane >> 2);
-            const bool valid = q < ns;
+        const bool warp_has_queries = (int)(threadIdx.x >> 5) * kDenseQueriesPerWarp < share;
+        for (int q0 = warp_has_queries ? warp_q0 : ns; q0 < ns; q0 += groups_total) {  // (warp-uniform trip count)
+            const int q = q0 + grp;
+            const bool valid = q < ns && has_query;
             if (q0 != warp_q0 && valid) pq = __ldg(src + q);
             double Pa = 0.0;
             int ca = 0;
@@ -490,7 +510,6 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
                 if (q0 == warp_q0) dense_axis_checked(sT + 4 * g, pdx, pdy, pdz, meta.origin[g], meta.cell, lo, hi, cs, Pa, ca);
                 else dense_axis(sT + 4 * g, pq, meta.origin[g], meta.cell, Pa, ca);
             }
-            const int lead = lane & ~(kGroup - 1);
             const double Px = __shfl_sync(kFull, Pa, lead), Py = __shfl_sync(kFull, Pa, lead + 1), Pz = __shfl_sync(kFull, Pa, lead + 2);
             const int cx = __shfl_sync(kFull, ca, lead), cy = __shfl_sync(kFull, ca, lead + 1), cz = __shfl_sync(kFull, ca, lead + 2);
             const int lim = (1 << 20) - 10;
@@ -501,24 +520,22 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
             if (g == 0 && valid && j >= 0 && j < 64 && (cx != pc.cx || cy != pc.cy || cz != pc.cz)) atomicAdd(&g_dense_mis[j], 1u);
 #endif
             if (q0 != warp_q0 || cx != pc.cx || cy != pc.cy || cz != pc.cz)
-                dense_load_plane(a, cx, cy, cz, g, valid && in_range && g < 3, pc);
+                dense_load_plane(a, cx, cy, cz, g, valid && in_range, pc);
             B2_DTS(10);
             B2_DTS_MAX(13);
-            dense_finish(a, sPivot, meta.cell, Px, Py, Pz, pc, valid, q, acc);
+            dense_finish(a, sPivot, meta.cell, Px, Py, Pz, pc, valid, q, g, lead, acc);
             B2_DTS(11);
         }
         // the group's column: rows by lane role
-        if (g == 0) {
-            sAccL[0][col] = acc[0]; sAccL[1][col] = acc[1]; sAccL[2][col] = acc[2];
-            sAccL[15][col] = acc[3]; sAccL[16][col] = acc[4];
-        } else {
-            const int ax = g - 1;
-            sAccL[3 + ax][col] = acc[0];
-            sAccL[6 + 3 * ax][col] = acc[1]; sAccL[7 + 3 * ax][col] = acc[2]; sAccL[8 + 3 * ax][col] = acc[3];
+        if (g < kDenseLanes) {
+            sAccL[3 + g][col] = acc[0];
+            sAccL[6 + 3 * g][col] = acc[1]; sAccL[7 + 3 * g][col] = acc[2]; sAccL[8 + 3 * g][col] = acc[3];
+            sAccL[g][col] = acc[4];
+            if (g < 2) sAccL[15 + g][col] = acc[5];
         }
     }
     __syncthreads();
     B2_DTS(4);
-    cta_fold<NT, kLeaders>(&sAccL[0][0], partial + ((size_t)wr * kCtasPerSm * kSMs + blockIdx.x) * kTerms);
+    cta_fold<NT, kDenseCols>(&sAccL[0][0], partial + ((size_t)wr * kCtasPerSm * kSMs + blockIdx.x) * kTerms);
     B2_DTS(5);
 }

@@ -17,6 +17,16 @@ Two map modes:
     anchored at a fixed voxel origin (the reference re-anchors at the growing map's
     min bound every scan, icp_processor.py:91) and ``global_map`` is the voxel
     centroids at ``map_voxel`` resolution, materialised on the host lazily.
+    ``construct_global_map`` / ``process`` only ENQUEUE a scan (the pose prior of the
+    next registration lives on the device, so nothing waits for the host); the poses
+    are read back when somebody looks: ``previous_transformation`` (any access),
+    ``last_result``, ``global_map`` — or after ``MAX_PENDING`` scans.  The reference
+    reads ``previous_transformation`` only inside ``align_point_clouds_with_icp``
+    (icp_processor.py:106,118), so the deferral is invisible to its callers; an error
+    of a deferred scan (map full, non-finite points) is raised at that read instead
+    of at the call.  A pageable scan array has been copied when the call returns; a
+    pinned (cudaHostAlloc / registered) array is read in place and must stay
+    unchanged until the poses have been read.
 
 ``mode="reference"``
     The reference's exact sequence (icp_processor.py:43-75,77-119) on GPU
@@ -33,7 +43,48 @@ from .generic_point_cloud_processor import ProcessPointClouds
 from .logging_shim import get_logger
 
 
+class _PoseLog(list):
+    """``previous_transformation`` of a resident-mode processor: a list that collects the poses of the scans
+    still in flight on the device before it lets anyone look (icp_processor.py:106,118 only ever reads [-1] and
+    appends; the GPU keeps its own copy of the pose prior, so registration never waits for the host)."""
+
+    def __init__(self, items, owner):
+        super().__init__(items)
+        self._owner = owner
+
+    def _sync(self):
+        owner = self._owner
+        if owner is not None and owner._pending_first:
+            owner.flush_results()
+
+    def __getitem__(self, i):
+        self._sync()
+        return super().__getitem__(i)
+
+    def __len__(self):
+        self._sync()
+        return super().__len__()
+
+    def __iter__(self):
+        self._sync()
+        return super().__iter__()
+
+    def __repr__(self):
+        self._sync()
+        return super().__repr__()
+
+    def __eq__(self, other):
+        self._sync()
+        return list.__eq__(self, other)
+
+    __hash__ = None
+
+
 class B200ICPProcessor(ProcessPointClouds):
+    # resident mode submits scans asynchronously; results are read back when somebody looks at them
+    # (previous_transformation, last_result, global_map) or when this many scans are pending
+    MAX_PENDING = 256
+
     def __init__(self, config_path: str, reset_event, data_transfer, *, mode: str = "resident",
                  voxel_size: float = 0.02, max_correspondence_distance: float | None = None,
                  max_iteration: int = 500, relative_fitness: float = 1e-6, relative_rmse: float = 1e-6,
@@ -45,7 +96,6 @@ class B200ICPProcessor(ProcessPointClouds):
         if maintenance not in ("voxel", "off", "full"):
             raise ValueError(f"unknown maintenance {maintenance!r}")
         self._map_cache = None
-        self._defer = False
         self._pending_first = []   # one flag per deferred scan: was it the first scan of the map?
         self._mode = mode
         self._engine = _lib.Engine(device)  # raises without CUDA / without the built library
@@ -59,9 +109,30 @@ class B200ICPProcessor(ProcessPointClouds):
         self._numpy2 = (int(np.__version__.split(".")[0]) >= 2) if numpy2_projection is None else bool(numpy2_projection)
         self._raw_map = None       # reference mode: CUDA float32 [N,4], newest scan first
         self._resident_ready = False
-        self.last_result = None    # b2_icp_result of the most recent registration
+        self._last_result = None   # b2_icp_result of the most recent registration
+        self._poses = _PoseLog([np.identity(4)], self)
         super().__init__(config_path, reset_event, data_transfer,
                          logger if logger is not None else get_logger("b200 icp processor"))
+
+    # -- results that may still be in flight -----------------------------------
+    @property
+    def previous_transformation(self):
+        return self._poses
+
+    @previous_transformation.setter
+    def previous_transformation(self, value):  # (the base class assigns [identity] in __init__ and reset())
+        self._pending_first = []
+        self._poses = _PoseLog(list(value), self)
+
+    @property
+    def last_result(self):
+        if self._pending_first:
+            self.flush_results()
+        return self._last_result
+
+    @last_result.setter
+    def last_result(self, value):
+        self._last_result = value
 
     # -- resuming from a resident map ------------------------------------------
     @property
@@ -84,14 +155,16 @@ class B200ICPProcessor(ProcessPointClouds):
     def set_pose_prior(self, T) -> None:
         """Seed the next registration (the role of previous_transformation[-1], icp_processor.py:106)."""
         T = np.array(T, dtype=np.float64).reshape(4, 4)
+        self.flush_results()
         self._engine.set_pose(T)
-        self.previous_transformation.append(T)
+        list.append(self._poses, T)
 
     # -- global_map: lazy device -> host materialisation ----------------------
     @property
     def global_map(self):
         if self._map_cache is None:
             if self._mode == "resident" and self._resident_ready and self.point_clouds_in_map > 0:
+                self.flush_results()
                 pts, _ = self._engine.map_export(want_keys=False)
                 self._map_cache = self._engine.unpack(pts) if pts.shape[0] else np.zeros((0, 3), np.float32)
             elif self._mode == "reference" and self._raw_map is not None:
@@ -125,27 +198,24 @@ class B200ICPProcessor(ProcessPointClouds):
 
     def process_records(self, scan, defer_result: bool = False) -> None:
         """The body of ``process()`` for a scan that has already been dequeued (``ProcessLoop`` drains the
-        input queue in batches).  ``defer_result=True`` (resident mode) only enqueues the
-        registration; ``flush_results()`` then appends the poses of all deferred scans to
-        ``previous_transformation`` with one device synchronisation for the whole batch."""
-        self._defer = bool(defer_result) and self._mode == "resident"
-        try:
-            self._process_records(scan)
-        finally:
-            self._defer = False
+        input queue in batches).  In resident mode a scan is only enqueued, whatever
+        ``defer_result`` says (kept for callers written against round 1); ``flush_results()`` appends the poses
+        of all pending scans to ``previous_transformation`` with one device synchronisation for the batch."""
+        del defer_result
+        self._process_records(scan)
 
     def flush_results(self) -> int:
         """Collect the results of the scans submitted with ``defer_result=True``; returns how many."""
-        n = len(self._pending_first)
+        pending, self._pending_first = self._pending_first, []  # (cleared first: a failed read-back must not
+        n = len(pending)                                         #  be retried against later scans' records)
         if n == 0:
             return 0
         results = self._engine.slam_results(n)
-        for first, res in zip(self._pending_first, results):
+        for first, res in zip(pending, results):
             if first:
                 continue  # the first scan is the map frame: no registration (icp_processor.py:53-56)
-            self.last_result = res
-            self.previous_transformation.append(res.matrix())
-        self._pending_first = []
+            self._last_result = res
+            list.append(self._poses, res.matrix())
         return n
 
     def _process_records(self, scan) -> None:
@@ -195,10 +265,11 @@ class B200ICPProcessor(ProcessPointClouds):
     def reset(self) -> None:
         self._pending_first = []
         if self._resident_ready:
+            self._engine.synchronize()
             self._engine.map_reset()
         self._raw_map = None
         self._map_cache = None
-        self.last_result = None
+        self._last_result = None
         super().reset()
 
     # -- resident mode --------------------------------------------------------
@@ -208,20 +279,18 @@ class B200ICPProcessor(ProcessPointClouds):
             eng.map_init(self._map_voxel, self._map_origin, self._max_corr, self._map_capacity)
             self._resident_ready = True
         first = self.point_clouds_in_map == 0
-        defer = self._defer and pts4 is not None
+        # enqueue only: upload, down-sample, ICP seeded with the pose kept on the device, fuse.  The pose comes
+        # back when somebody reads previous_transformation / last_result / global_map (or MAX_PENDING is reached);
+        # a pageable `pts` has been copied into the library's pinned ring when the call returns
         if pts4 is not None:
-            res = eng.slam_scan_dev(pts4, self._voxel, self._params, want_result=not defer)
+            eng.slam_scan_dev(pts4, self._voxel, self._params, want_result=False)
         else:
-            res = eng.slam_scan(pts, self._voxel, self._params)
-        if defer:
-            self._pending_first.append(first)
+            eng.slam_scan(pts, self._voxel, self._params, want_result=False)
+        self._pending_first.append(first)
         if first:
             self.point_clouds_in_map += 1  # icp_processor.py:54 (the caller increments once more)
-            return
-        if defer:
-            return
-        self.last_result = res
-        self.previous_transformation.append(res.matrix())
+        if len(self._pending_first) >= self.MAX_PENDING:
+            self.flush_results()
 
     # -- reference mode -------------------------------------------------------
     def _construct_reference(self, scan4) -> None:
@@ -236,9 +305,9 @@ class B200ICPProcessor(ProcessPointClouds):
         # icp_processor.py:94-99 estimates normals on both clouds here and never uses them
         # (point-to-point estimation): skipped, the result does not depend on them.
         res, _ = eng.icp(source_down, target_down, self._params, init=self.previous_transformation[-1])
-        self.last_result = res
+        self._last_result = res
         T = res.matrix()
-        self.previous_transformation.append(T)
+        list.append(self._poses, T)
         moved = eng.transform(scan4, T)
         with torch.cuda.stream(eng.stream):
             self._raw_map = torch.cat([moved, self._raw_map], dim=0)

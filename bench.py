@@ -262,16 +262,19 @@ def run_ours(args):
         for k in range(b, b + S):
             eng.slam_scan_dev(dev_scans[k], DS_VOXEL, prm)
 
-    def step_plugin():
+    def step_plugin(per_scan_wait=False):
         """The same stretch through the reference's plugin entry point with the arrays a ROS callback holds:
-        ordinary (pageable) float32 [N,3] NumPy scans in, the registered pose of every scan back on the host
-        (previous_transformation[-1]) before the next call."""
+        ordinary (pageable) float32 [N,3] NumPy scans in; the registered poses of the step's scans are read back
+        on the host at the end of the step (previous_transformation: one device->host read of S result records),
+        or — per_scan_wait — after every call, before the next scan is submitted."""
         b = (step_no[2] % n_seg) * S
         step_no[2] += 1
         proc.set_pose_prior(poses[b])
         for k in range(b, b + S):
             proc.construct_global_map(scans[k])
             proc.point_clouds_in_map += 1  # ProcessPointClouds.process does this after every call (:126)
+            if per_scan_wait:
+                proc.previous_transformation[-1]
         return proc.last_result, proc.previous_transformation[-1], poses[b + S - 1]
 
     def step_cabi(per_scan_sync=False):
@@ -319,6 +322,13 @@ def run_ours(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     e2e_value = world * S * args.steps / (e2e_ms / 1e3)
     err = float(np.linalg.norm(last_T[:3, 3] - last_pose[:3, 3]))  # pose accuracy vs the synthetic truth (sanity)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        step_plugin(per_scan_wait=True)
+    eng.synchronize()
+    barrier()
+    plugin_sync = world * S * max(1, args.steps // 2) / max_over_ranks(time.perf_counter() - t0)
 
     # ---- the bare C-ABI with pinned scans: deferred results, then a host wait after every scan
     for _ in range(max(1, args.warmup // 2)):
@@ -354,9 +364,13 @@ def run_ours(args):
                      "mean_fitness": round(fit, 4), "final_pose_error_m": round(err, 4),
                      "distinct_scan_bytes": S * n_seg * SCAN_POINTS * 16},
         "e2e": {"value": round(e2e_value, 2), "unit": "scans/s",
-                "path": "B200ICPProcessor.construct_global_map(points) per scan, pageable float32 [N,3] NumPy input, "
-                        "pose of every scan on the host before the next call",
+                "path": "B200ICPProcessor.construct_global_map(points) per scan, pageable float32 [N,3] NumPy input "
+                        "(H2D of every scan inside); the poses of the step's S scans are read back on the host at the "
+                        "end of every step (previous_transformation)",
                 "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
+                "plugin_per_scan_wait_value": round(plugin_sync, 2),
+                "plugin_per_scan_wait_note": "the same calls with previous_transformation[-1] read after EVERY scan "
+                                             "(a live node that needs each pose before it submits the next scan)",
                 "cabi_pinned_deferred_value": round(cabi_deferred, 2),
                 "cabi_pinned_per_scan_wait_value": round(cabi_sync, 2),
                 "cabi_note": "b2_slam_scan with pinned host scans; deferred = out == NULL for the S scans of a step, then "
@@ -473,11 +487,30 @@ def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2b
         ms_all.append(max_over_ranks(ev[0].elapsed_time(ev[2])))
         ms_gather.append(max_over_ranks(ev[1].elapsed_time(ev[2])))
     ms = float(np.median(ms_all))
+    # the collective alone: every rank enters it at the same moment (barrier first), so what is timed is the
+    # all-gather itself and not the wait for the slowest rank's batch (that wait is part of `ms` and is what
+    # ms_gather_in_run shows)
+    local = allres[b:e] if world > 1 else allres
+    local = local.clone()
+    ms_gather_alone = []
+    for _ in range(5):
+        barrier()
+        with torch.cuda.stream(eng.stream):
+            ev[0].record()
+            gatherer.gather(local)
+            ev[1].record()
+        eng.synchronize()
+        ms_gather_alone.append(max_over_ranks(ev[0].elapsed_time(ev[1])))
     rec = b2batch.records_view(allres, eng)
     out = {"metric": "batched pair-ICP/s", "value": round(n_total / (ms / 1e3), 2), "unit": "pairs/s",
            "scaling": "strong", "pairs_total": n_total, "pairs_this_rank": P, "distinct_pairs_per_rank": distinct,
            "ms": round(ms, 3), "ms_all_reps": [round(x, 3) for x in ms_all],
-           "gather_ms": round(float(np.median(ms_gather)), 4), "gathered_records": int(len(rec)),
+           "gather_ms": round(float(np.median(ms_gather_alone)), 4),
+           "gather_in_run_ms": round(float(np.median(ms_gather)), 4),
+           "gather_note": "gather_ms = the all-gather alone, ranks aligned by a barrier; gather_in_run_ms = from the end of "
+                          "this rank's batch to the end of the collective inside the timed run, i.e. it includes waiting "
+                          "for the slowest rank's batch (ranks register different pairs)",
+           "gathered_records": int(len(rec)),
            "mean_fitness": round(float(rec["fitness"].mean()), 4),
            "collective": "all_gather_into_tensor of 152 B/pair result records (pre-allocated buffers)"
                          if world > 1 else "none (1 rank)"}

@@ -61,3 +61,48 @@ def test_gpu_against_golden_pins(engine, b2, pair0):
     assert digest(sk.cpu().numpy()) == g["src_keys_sha"]
     assert digest(sd.cpu().numpy()[:, :3]) == g["src_centroids_f32_sha"]
     assert digest(sd.cpu().numpy()[:, 3].copy().view(np.int32)) == g["src_counts_sha"]
+
+
+O3D_PINS = os.path.join(os.path.dirname(__file__), "golden", "open3d_pins.json")
+
+
+@pytest.mark.skipif(not os.path.exists(O3D_PINS),
+                    reason="tests/golden/open3d_pins.json not generated yet (needs a machine with Open3D: "
+                           "python tests/golden/make_open3d_golden.py) — parity stays UNPINNED until then")
+def test_oracle_against_open3d_pins(pair0):
+    """The oracle against outputs of the real Open3D calls of icp_processor.py:90-113,130-146 on the same seeded
+    inputs.  Integer / index outputs bit-exact (exact-distance ties aside), floating point within 1e-9."""
+    g = json.load(open(O3D_PINS))
+    src, tgt, T_true = pair0
+    assert digest(src) == g["inputs"]["src_sha"] and digest(tgt) == g["inputs"]["tgt_sha"]
+    s64, t64 = src.astype(np.float64), tgt.astype(np.float64)
+    sd, sk, _ = cpu.voxel_downsample(s64, 0.02)
+    td, tk, _ = cpu.voxel_downsample(t64, 0.02)
+    v = g["voxel_0.02"]
+    assert (len(sk), len(tk)) == (v["n_src"], v["n_tgt"])
+    assert digest(sk) == v["src_keys_sha"]
+    np.testing.assert_allclose(sd[:5], np.array(v["src_centroids_first5"]), rtol=0, atol=1e-12)
+    assert digest(sd.astype(np.float32)) == v["src_centroids_f32_sha"]
+    fused, fk, _ = cpu.voxel_downsample(np.concatenate([t64, cpu.transform(s64, T_true)]), 0.05,
+                                        origin=[-9.0, -9.0, -9.0])
+    assert len(fk) == g["fuse_0.05"]["n"] and digest(fk) == g["fuse_0.05"]["keys_sha"]
+    np.testing.assert_allclose(fused[:5], np.array(g["fuse_0.05"]["centroids_first5"]), rtol=0, atol=1e-12)
+    idx, _ = cpu.nn_search(sd, td, 0.05)
+    assert int((idx >= 0).sum()) == g["nn_0.05"]["n_corr"] and digest(idx) == g["nn_0.05"]["idx_sha"]
+    r = cpu.registration_icp(sd, td, 0.05, max_iteration=30)
+    p = g["icp_p2p_30"]
+    np.testing.assert_allclose(r.transformation, np.array(p["T"]), rtol=0, atol=1e-9)
+    assert r.iterations == p["iterations"] and r.fitness == p["fitness"]
+    assert r.inlier_rmse == pytest.approx(p["rmse"], rel=1e-9)
+    assert digest(r.correspondence) == p["corr_sha"]
+    nrm = cpu.estimate_normals(td, 0.04, 20)
+    np.testing.assert_allclose(np.abs(nrm[:5]), np.array(g["normals_first5"]), atol=1e-9)
+    r2 = cpu.registration_icp(sd, td, 0.05, mode="p2l", tgt_normals=nrm, max_iteration=30)
+    np.testing.assert_allclose(r2.transformation, np.array(g["icp_p2l_30"]["T"]), rtol=0, atol=1e-7)
+    assert r2.fitness == g["icp_p2l_30"]["fitness"]
+    cloud = np.concatenate([td, sd])
+    for name, mask in (("sor_45_3.5", cpu.statistical_outlier_mask(cloud, 45, 3.5)),
+                       ("sor_80_2.0", cpu.statistical_outlier_mask(cloud, 80, 2.0)),
+                       ("ror_8_0.023", cpu.radius_outlier_mask(cloud, 8, 0.023))):
+        assert int(mask.sum()) == g[name]["kept"], name
+        assert digest(mask.astype(np.uint8)) == g[name]["mask_sha"], name
