@@ -448,8 +448,11 @@ bool stream_applicable(int n_max);
 int stream_begin(Context* c, int n_max);
 int stream_downsample(Context* c, const float4* pts, int n_max, const int* n_dev, double voxel, float4* out_pts,
                       int* out_count_dev);
+// btab != null (brick-major map): the collecting pass also creates the bricks of the scan's voxels
 int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev,
-                         const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out);
+                         const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out,
+                         BrickEntry* btab, unsigned bmask, unsigned long long* bkeys, unsigned pool_bricks,
+                         long long* counters);
 
 // b2_map.cu
 void map_free(Context* c);

@@ -495,8 +495,18 @@ int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, 
     B2_WS(c, dkeys, int, WS_TMP_KEYS, sizeof(int) * 3 * (size_t)n_max);
     B2_WS(c, dsums, double, WS_SUMS, sizeof(double) * 4 * (size_t)n_max);
     SortCtl* ctl = nullptr;
-    B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl));
-    B2_TRY(merge_launch(c, m, dkeys, dsums, ctl, n_max));
+    if (m->brick == 1) {  // the collecting pass creates the bricks: only the merge is left
+        B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl, m->btab,
+                                    m->capacity - 1, m->bkeys, m->pool_bricks, m->counters));
+        pdl_launch(brick_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
+                   (const double*)dsums, (const SortCtl*)ctl, (const BrickEntry*)m->btab, m->capacity - 1, m->cent, m->acc,
+                   m->counters, m->max_voxels, c->dev_status);
+        B2_LAUNCH_CHECK(c);
+    } else {
+        B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl, nullptr, 0,
+                                    nullptr, 0, nullptr));
+        B2_TRY(merge_launch(c, m, dkeys, dsums, ctl, n_max));
+    }
     m->host_voxels_bound += n_max;
     return B2_OK;
 }

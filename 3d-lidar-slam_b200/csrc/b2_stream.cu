@@ -16,12 +16,13 @@
 //                  order), which keeps the queries of an ICP CTA spatially together like the key order did.
 //   fuse         : fuse_scatter (P = T p, q = (P - origin) / v, key = floor(q), insert, 64-bit FIXED-POINT
 //                  atomicAdd of frac(q) at 2^-40 voxel: order-independent, hence deterministic) -> fuse_collect
-//                  (occupied slots -> (key, sum, count) records; sum = n * corner + v * sum frac) -> the map's own
-//                  brick_ensure + merge kernels (b2_map.cu: one thread per unique voxel, fp64 accumulators).
+//                  (occupied slots -> (key, sum, count) records; sum = n * corner + v * sum frac; creates the
+//                  voxel's brick if the map has none yet) -> the map's own merge kernel (b2_map.cu: one thread per
+//                  unique voxel, fp64 accumulators; its last thread block also commits the registered pose).
 //                  The per-scan sums differ from in-order fp64 sums by ~1e-15 relative (far inside the 1e-5
 //                  centroid tolerance); keys and counts are exact.
 //
-// 4 + 4 launches instead of 15 + 13.  One zero-fill clears both tables, the bounding box and the scan state.
+// 3 + 3 launches instead of 15 + 13.  One zero-fill clears both tables, the bounding box and the scan state.
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -242,13 +243,18 @@ fuse_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_de
     atomicAdd(&t.cnt[h], 1u);
 }
 
-// Occupied slots -> (voxel key, (sum x, sum y, sum z, count)) records for the map's merge kernels.
+// Occupied slots -> (voxel key, (sum x, sum y, sum z, count)) records for the map's merge kernel.  When the map is
+// brick-major (btab != null) the thread also makes sure the voxel's brick exists (the work of brick_ensure_kernel:
+// the winner of the key CAS takes the next pool brick and publishes its index; nobody waits for it here, the merge
+// is a separate launch).
 __global__ void __launch_bounds__(kBlock)
 fuse_collect_kernel(ScanTable t, double ox, double oy, double oz, double voxel, int* __restrict__ keys3,
-                    double* __restrict__ sums, StreamHead* __restrict__ head) {
+                    double* __restrict__ sums, StreamHead* __restrict__ head, BrickEntry* __restrict__ btab,
+                    unsigned bmask, unsigned long long* __restrict__ bkeys, unsigned pool_bricks,
+                    long long* __restrict__ counters, int* __restrict__ dev_status) {
     pdl_enter();
     const unsigned h = blockIdx.x * kBlock + threadIdx.x;
-    const unsigned long long key = h <= t.mask ? t.keys[h] : 0ull;
+    const unsigned long long key = (h <= t.mask && *dev_status == 0) ? t.keys[h] : 0ull;
     const bool occ = key != 0ull;
     const unsigned ball = __ballot_sync(0xffffffffu, occ);
     if (ball == 0u) return;
@@ -273,6 +279,27 @@ fuse_collect_kernel(ScanTable t, double ox, double oy, double oz, double voxel, 
         sums[4 * j + d] = dadd(dmul(dn, corner), dmul(dmul((double)(long long)s[d], kFixInv), voxel));
     }
     sums[4 * j + 3] = dn;
+    if (btab) {
+        const unsigned long long bkey = map_cell_key(kx >> 3, ky >> 3, kz >> 3);  // (arithmetic shift = floor / 8)
+        unsigned bh = cell_hash(bkey) & bmask;
+        for (unsigned probe = 0; probe < 4096u; ++probe) {
+            unsigned long long cur = btab[bh].key;
+            if (cur == kEmptyKey) cur = atomicCAS(&btab[bh].key, kEmptyKey, bkey);
+            if (cur == kEmptyKey) {  // created here
+                const unsigned long long idx = (unsigned long long)atomicAdd((unsigned long long*)&counters[0], 1ull);
+                if (idx >= pool_bricks) {
+                    atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+                    return;
+                }
+                bkeys[idx] = bkey;
+                btab[bh].index = (unsigned)idx;
+                return;
+            }
+            if (cur == bkey) return;
+            bh = (bh + 1) & bmask;
+        }
+        atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+    }
 }
 
 unsigned table_slots(int n_max) {
@@ -349,14 +376,17 @@ int stream_downsample(Context* c, const float4* pts, int n_max, const int* n_dev
 // The (key, sum, count) records of voxel_down_sample(T * pts, voxel) at an explicit origin, sort-free:
 // keys3 [n_max,3], sums [n_max,4], count in *ctl_out->nseg.  stream_begin() must have run in this step.
 int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev,
-                         const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out) {
+                         const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out,
+                         BrickEntry* btab, unsigned bmask, unsigned long long* bkeys, unsigned pool_bricks,
+                         long long* counters) {
     StreamBuffers sb;
     B2_TRY(stream_buffers(c, n_max, &sb));
     pdl_launch(fuse_scatter_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, pts, n_dev, n_max, T_dev,
                origin[0], origin[1], origin[2], voxel, sb.fuse, c->dev_status);
     B2_LAUNCH_CHECK(c);
     pdl_launch(fuse_collect_kernel, dim3(div_up((long long)sb.fuse.mask + 1, kBlock)), dim3(kBlock), c->stream, sb.fuse,
-               origin[0], origin[1], origin[2], voxel, keys3, sums, sb.head);
+               origin[0], origin[1], origin[2], voxel, keys3, sums, sb.head, btab, bmask, bkeys, pool_bricks, counters,
+               c->dev_status);
     B2_LAUNCH_CHECK(c);
     *ctl_out = &sb.head->ctl;
     return B2_OK;

@@ -27,7 +27,9 @@ Keys of the JSON line (rank 0 prints exactly one):
                    per-scan rebuild (oracle.cpp: ResidentMap).
   batched_pairs    config 5: 8192 independent scan pairs split over the ranks (STRONG scaling), one NCCL
                    all-gather of the 152-byte result records inside the timed region.
-  streaming        config 4 (with --streaming, or benchmarks/stream_replay.py): 1000-frame replay.
+  streaming        config 4 (benchmarks/stream_replay.py in a child process): 1000-frame replay through the plugin,
+                   resumed on an ~8 M-voxel map (map tables far beyond L2); sustained scans/s, first vs last 100
+                   frames, map size over time, drift.
 --impl reference : the reference's own CPU sequence restated on the oracle port (Open3D is not installable
                    here), same scene / map / scans / parameters, every step a bounded sample of
                    `--ref-scans-per-step` scans.
@@ -81,8 +83,8 @@ def parse_args():
     ap.add_argument("--ref-scans-per-step", type=int, default=2, help="--impl reference: scans per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batched", action="store_true")
-    ap.add_argument("--streaming", type=int, default=0, metavar="FRAMES",
-                    help="also run the config-4 streaming replay with this many frames (N = 1 only)")
+    ap.add_argument("--streaming", type=int, default=1000, metavar="FRAMES",
+                    help="config 4: streaming replay of this many frames resumed on an ~8 M-voxel map (N = 1 only; 0 skips)")
     return ap.parse_args()
 
 
@@ -559,7 +561,8 @@ def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2b
 
 def run_streaming(frames: int):
     """Config 4 through benchmarks/stream_replay.py in a child process (its own engine and map)."""
-    cmd = [sys.executable, os.path.join(ROOT, "benchmarks", "stream_replay.py"), "--frames", str(frames), "--quiet"]
+    cmd = [sys.executable, os.path.join(ROOT, "benchmarks", "stream_replay.py"), "--frames", str(frames), "--quiet",
+           "--preload-length", "800", "--capacity", str(1 << 24), "--deferred"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     for ln in reversed(r.stdout.strip().splitlines()):
         if ln.startswith("{"):
