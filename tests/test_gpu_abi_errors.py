@@ -78,3 +78,26 @@ def test_call_order_and_map_limits(raw, b2):
     assert lib.b2_slam_results(h, 2, (b2.IcpResult * 2)()) == INVALID      # only one scan registered so far
     assert lib.b2_slam_results(h, 1, (b2.IcpResult * 1)()) == 0
     assert lib.b2_map_size(h, C.byref(size)) == 0 and size.value > 0
+
+
+def test_scan_path_and_scan_downsample_arguments(raw, b2):
+    """Round-2 entry points: b2_set_scan_path and b2_scan_downsample reject what they cannot serve; a scan with a
+    non-finite coordinate has no voxel (Open3D's int32 voxel index is undefined for it): B2_ERR_KEY_RANGE."""
+    eng, lib, h = raw
+    assert lib.b2_set_scan_path(h, 7) == INVALID and "scan_path" in _err(lib, h)
+    assert lib.b2_set_scan_path(h, 1) == 0 and lib.b2_set_scan_path(h, 0) == 0
+    pts = eng.pack(np.random.default_rng(3).normal(size=(500, 3)).astype(np.float32))
+    out = eng.empty_points(500)
+    n = C.c_int(-1)
+    assert lib.b2_scan_downsample(h, None, 500, 0.02, out.data_ptr(), C.byref(n)) == INVALID
+    assert lib.b2_scan_downsample(h, pts.data_ptr(), 500, 0.0, out.data_ptr(), C.byref(n)) == INVALID
+    assert lib.b2_scan_downsample(h, pts.data_ptr(), 500, 0.02, out.data_ptr(), None) == INVALID
+    big = 200_000  # beyond the single-scan limit of the look-back scan (one 1024-point block per SM)
+    assert lib.b2_scan_downsample(h, pts.data_ptr(), big, 0.02, out.data_ptr(), C.byref(n)) == INVALID
+    assert "b2_voxel_downsample" in _err(lib, h)
+    assert lib.b2_scan_downsample(h, pts.data_ptr(), 0, 0.02, out.data_ptr(), C.byref(n)) == 0 and n.value == 0
+    bad = np.random.default_rng(4).normal(size=(500, 3)).astype(np.float32)
+    bad[123, 1] = np.nan
+    assert lib.b2_scan_downsample(h, eng.pack(bad).data_ptr(), 500, 0.02, out.data_ptr(), C.byref(n)) == -4  # KEY_RANGE
+    # the handle is usable again
+    assert lib.b2_scan_downsample(h, pts.data_ptr(), 500, 0.02, out.data_ptr(), C.byref(n)) == 0 and 0 < n.value <= 500

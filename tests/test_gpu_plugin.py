@@ -200,3 +200,87 @@ def test_process_loop_batches_scans_through_the_real_processor():
     published = dta.global_map_queue.get(timeout=5)
     assert published.shape[1] == 3 and len(published) > 1000
     np.testing.assert_array_equal(a.global_map, b.global_map)
+
+
+def test_resident_mode_is_asynchronous_and_synchronises_on_observation():
+    """Resident mode only enqueues a scan: the poses arrive when previous_transformation /
+    last_result / global_map are read.  Whatever the read pattern, the results are those of the scan-by-scan
+    synchronous C-ABI run, bit for bit (icp_processor.py:106,118: the reference reads the list only inside ICP)."""
+    import lidar_slam_b200 as b2
+
+    scans = _scans(12, seed=6)
+    eng = b2.Engine(0)
+    eng.map_init(0.02, [0.0, 0.0, 0.0], 0.05, 1 << 20)
+    prm = b2.make_params(0.05, 30)
+    want = [eng.slam_scan(s, 0.02, prm).matrix() for s in scans]
+    eng.close()
+    for read_every in (1, 5, 100):
+        proc, _ = _processor(mode="resident", max_iteration=30, map_capacity_cells=1 << 20)
+        for k, s in enumerate(scans):
+            proc.construct_global_map(s)
+            proc.point_clouds_in_map += 1
+            if (k + 1) % read_every == 0:
+                assert len(proc.previous_transformation) == k + 1      # identity + k registrations (first scan: none)
+        assert len(proc._pending_first) == (0 if read_every == 1 else len(scans) % read_every)
+        assert proc.last_result is not None and proc.last_result.fitness > 0.9   # (reading flushes)
+        assert not proc._pending_first
+        got = list(proc.previous_transformation)
+        assert len(got) == len(scans)
+        np.testing.assert_array_equal(got[0], np.eye(4))
+        for k in range(1, len(scans)):
+            np.testing.assert_array_equal(got[k], want[k])
+        assert proc.global_map.shape[1] == 3 and len(proc.global_map) > 1000
+        proc.reset()
+        assert len(proc.previous_transformation) == 1 and proc.last_result is None and proc.point_clouds_in_map == 0
+        proc.engine.close()
+
+
+def test_pageable_scans_are_copied_before_the_call_returns():
+    """b2_slam_scan stages a pageable array through the library's pinned ring: the caller may overwrite or free
+    it as soon as the call returns, even though the scan has only been enqueued.  Same results as pinned input."""
+    import torch
+
+    scans = _scans(10, seed=7)
+    runs = []
+    for kind in ("pinned", "pageable-clobbered"):
+        proc, _ = _processor(mode="resident", max_iteration=30, map_capacity_cells=1 << 20)
+        keep = []
+        for s in scans:
+            if kind == "pinned":
+                a = torch.from_numpy(s.copy()).pin_memory().numpy()
+                keep.append(a)                       # a pinned array is read in place: keep it alive and unchanged
+                proc.construct_global_map(a)
+            else:
+                a = s.copy()
+                proc.construct_global_map(a)
+                a[:] = np.nan                        # clobber right away
+            proc.point_clouds_in_map += 1
+        runs.append([T.copy() for T in proc.previous_transformation])
+        proc.engine.close()
+    assert len(runs[0]) == len(runs[1]) == len(scans)
+    for a, b in zip(*runs):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_deferred_errors_surface_at_the_read_and_leave_the_processor_usable():
+    """A scan the device cannot voxelise (a NaN coordinate) fails asynchronously: construct_global_map returns,
+    the B2Error is raised where the poses are read, nothing of that scan is committed, and later scans work."""
+    import lidar_slam_b200 as b2
+
+    scans = _scans(4, seed=8)
+    proc, _ = _processor(mode="resident", max_iteration=30, map_capacity_cells=1 << 20)
+    proc.construct_global_map(scans[0]); proc.point_clouds_in_map += 1
+    proc.construct_global_map(scans[1]); proc.point_clouds_in_map += 1
+    assert len(proc.previous_transformation) == 2
+    size_before = proc.engine.map_size()
+    bad = scans[2].copy()
+    bad[17, 2] = np.nan
+    proc.construct_global_map(bad)                   # enqueued; no error yet
+    with pytest.raises(b2.B2Error):
+        len(proc.previous_transformation)
+    assert not proc._pending_first                   # not retried against later scans' records
+    assert proc.engine.map_size() == size_before     # the failed scan touched neither map ...
+    np.testing.assert_array_equal(proc.engine.get_pose(), proc.previous_transformation[-1])  # ... nor pose
+    proc.construct_global_map(scans[2]); proc.point_clouds_in_map += 1
+    assert len(proc.previous_transformation) == 3 and proc.last_result.fitness > 0.9
+    proc.engine.close()

@@ -210,3 +210,36 @@ def test_hash_and_sorted_scan_paths_register_and_fuse_alike(b2):
     np.testing.assert_array_equal(ka, kb)
     np.testing.assert_array_equal(ca[:, 3].copy().view(np.int32), cb[:, 3].copy().view(np.int32))
     np.testing.assert_allclose(ca[:, :3], cb[:, :3], rtol=1e-6, atol=1e-6)
+
+
+def test_hash_scan_path_on_a_slab_map_matches_the_resident_cpu_map(b2):
+    """The reference's default geometry (2 cm voxels, 5 cm gate: a map of 3^3-voxel cells, the slab layout and the
+    group ICP kernel) through the sort-free scan step, against the resident CPU map of the oracle fed the same scans
+    (icp_processor.py:43-119): iterations and fitness equal, poses within 1e-4, identical voxel keys and counts."""
+    from conftest import assert_transform_close
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(12, length=12.0)
+    poses = synth.corridor_trajectory(scene, 5, seed=12, step=0.02)
+    scans = [synth.render_scan(scene, p, seed=40 + k).numpy()[::2].copy() for k, p in enumerate(poses)]
+    origin = [-20.0, -20.0, -20.0]
+    eng = b2.Engine(0)
+    eng.map_init(0.02, origin, 0.05, 1 << 19)
+    cpu_map = orc.ResidentMapCPU(0.02, origin, ds_voxel=0.02, max_corr=0.05, max_iteration=30)
+    prm = b2.make_params(0.05, 30)
+    for k, s in enumerate(scans):
+        res = eng.slam_scan(s, 0.02, prm)
+        ores = cpu_map.process(s)
+        if k == 0:
+            assert ores is None
+            continue
+        assert res.iterations == ores.iterations and res.fitness == ores.fitness, k
+        assert_transform_close(res.matrix(), ores.transformation)
+    cent, keys = eng.map_export()
+    oc, ok, on = cpu_map.map_points()
+    np.testing.assert_array_equal(keys.cpu().numpy(), ok)
+    c = cent.cpu().numpy()
+    np.testing.assert_array_equal(c[:, 3].copy().view(np.int32), on)
+    np.testing.assert_allclose(c[:, :3], oc, rtol=1e-5, atol=1e-5)
+    cpu_map.close()
+    eng.close()
