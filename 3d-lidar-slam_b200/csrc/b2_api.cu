@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 
 #include "b2_common.cuh"
 
@@ -254,7 +255,11 @@ int b2_create(int device, b2_handle* out) {
     Context* c = new Context();
     c->scan_path = getenv("B2_STREAM_SORTED") ? B2_SCAN_PATH_SORTED : B2_SCAN_PATH_HASH;
     c->device = device;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // the main stream (ICP chain, fusion) outranks the front stream (uploads, down-sample of the NEXT scan), whose
+    // CTAs only fill what the ICP chain leaves free
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         delete c;
         return B2_ERR_CUDA;
     }
@@ -265,11 +270,12 @@ int b2_create(int device, b2_handle* out) {
         delete c;
         return B2_ERR_CUDA;
     }
-    bool aux_ok = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+    bool aux_ok = cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
                   cudaHostAlloc(&c->result_ring, sizeof(IcpResultDev) * kResultRing, cudaHostAllocDefault) == cudaSuccess &&
                   cudaHostAlloc((void**)&c->count_ring, sizeof(int) * kResultRing, cudaHostAllocDefault) == cudaSuccess;
     for (int i = 0; i < 4 && aux_ok; ++i)
         aux_ok = cudaEventCreateWithFlags(&c->ev_block[i], cudaEventDisableTiming) == cudaSuccess;
+    aux_ok = aux_ok && cudaEventCreateWithFlags(&c->ev_dev_ready, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && aux_ok; ++i)
         aux_ok = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&c->ev_consumed[i], cudaEventDisableTiming) == cudaSuccess;
@@ -294,7 +300,10 @@ int b2_create(int device, b2_handle* out) {
 int b2_destroy(b2_handle h) {
     CTX(h);
     cudaStreamSynchronize(c->stream);
-    if (c->scan_graph.exec) cudaGraphExecDestroy(c->scan_graph.exec);
+    for (int i = 0; i < 2; ++i) {
+        if (c->front_graph[i].exec) cudaGraphExecDestroy(c->front_graph[i].exec);
+        if (c->main_graph[i].exec) cudaGraphExecDestroy(c->main_graph[i].exec);
+    }
     map_free(c);
     for (auto& b : c->ws)
         if (b.p) cudaFree(b.p);
@@ -306,6 +315,7 @@ int b2_destroy(b2_handle h) {
         cudaEventDestroy(c->ev_consumed[i]);
     }
     cudaStreamDestroy(c->copy_stream);
+    if (c->ev_dev_ready) cudaEventDestroy(c->ev_dev_ready);
     for (int i = 0; i < Context::kHostStages; ++i) {
         if (c->host_stage[i]) cudaFreeHost(c->host_stage[i]);
         if (c->ev_host_stage[i]) cudaEventDestroy(c->ev_host_stage[i]);
@@ -510,9 +520,12 @@ int b2_scan_downsample(b2_handle h, const float* pts_dev, int n, double voxel, f
     if (n == 0) return B2_OK;
     if (!stream_applicable(n))
         return set_error(c, B2_ERR_INVALID, "b2_scan_downsample: %d points exceed the single-scan limit (use b2_voxel_downsample)", n);
-    B2_TRY(stream_begin(c, n));
+    // (the scan tables are shared with the down-samples of deferred scans still in flight on the front stream)
+    B2_CUDA_OK(c, cudaStreamSynchronize(c->copy_stream));
+    B2_TRY(stream_begin_pre(c, n, 0));
     B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
-    B2_TRY(stream_downsample(c, (const float4*)pts_dev, n, nullptr, voxel, (float4*)out_pts_dev, cnt));
+    B2_TRY(stream_downsample(c, (const float4*)pts_dev, n, nullptr, voxel, (float4*)out_pts_dev, cnt, 0));
+    B2_TRY(stream_propagate_status(c, n, 0));
     int* hn = (int*)c->host_mailbox;
     B2_CUDA_OK(c, cudaMemcpyAsync(hn, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     B2_TRY(check_status(c));
@@ -797,61 +810,101 @@ static void slam_resync_after_failure(Context* c) {
     if (map_counts(c, nullptr, &voxels) == B2_OK) map_set_voxels_bound(c, voxels);
 }
 
-// Everything of one scan step after the scan sits in the fixed device buffer `scan`:
-// down-sample -> ICP against the resident map (pose chained on the device) -> fuse.
-static int slam_body(Context* c, const float4* scan, int n, const int* n_dev, double ds_voxel,
-                     const b2_icp_params* params, bool map_empty) {
+// ---- the scan step -----------------------------------------------------------------------------------------------
+// Two halves on two streams, double-buffered by scan parity `par`:
+//   front (c->copy_stream): upload + pack of the scan into scan[par], its live point count into n_dev[par], and —
+//          sort-free path, map not empty — its 2 cm down-sample into sdown[par] / cnt[par].  None of this depends on
+//          the map or on the previous pose, so with a caller that runs ahead (out == NULL) the front half of scan k+1
+//          runs while scan k is still being registered: its kernels are small (128-thread CTAs fit next to the
+//          one 640-thread ICP CTA of an SM) and live in the shadow of the ICP chain.
+//   main  (c->stream): ICP of sdown[par] against the resident map seeded with the pose kept on the device, fusion of
+//          scan[par] with the registered pose, pose commit.
+// ev_copied[par]: front -> main (the buffers of `par` are filled); ev_consumed[par]: main -> front (they may be
+// reused, two scans later).  A failed down-sample leaves its reason in the parity's status word; the fusion of the
+// same scan hands it to the sticky status word, so a failure of scan k+1 cannot be blamed on scan k.
+struct StreamSwap {  // the internal launchers use c->stream: the front half runs them on the front stream
+    Context* c;
+    cudaStream_t saved;
+    StreamSwap(Context* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
+
+struct ScanBuffers {
+    float4* scan;   // [cap] the raw scan, packed
+    int* n_dev;     // live point count
+    float4* sdown;  // [cap] down-sampled source
+    int* cnt;       // its size
+};
+
+static int scan_buffers(Context* c, int cap, int par, ScanBuffers* sb) {
+    B2_WS(c, scan, float4, par ? WS_SCAN_PTS2 : WS_SCAN_PTS, sizeof(float4) * (size_t)cap);
+    B2_WS(c, counts, int, WS_SCAN_COUNT, sizeof(int) * 16);
+    B2_WS(c, sdown, float4, par ? WS_SRC_DOWN2 : WS_SRC_DOWN, sizeof(float4) * (size_t)cap);
+    sb->scan = scan;
+    sb->n_dev = counts + 4 * par;
+    sb->cnt = counts + 8 + 4 * par;
+    sb->sdown = sdown;
+    return B2_OK;
+}
+
+static bool scan_fast(Context* c, int n) { return c->scan_path == B2_SCAN_PATH_HASH && stream_applicable(n); }
+
+// front half after the scan sits in scan[par] (launches on c->stream = the front stream while it runs)
+static int slam_front_body(Context* c, const ScanBuffers& sb, int n, double ds_voxel, int par) {
+    B2_TRY(stream_begin_pre(c, n, par));
+    B2_TRY(stream_downsample(c, sb.scan, n, sb.n_dev, ds_voxel, sb.sdown, sb.cnt, par));
+    return B2_OK;
+}
+
+// main half: ICP against the resident map (pose chained on the device) -> fuse -> pose commit
+static int slam_main_body(Context* c, const ScanBuffers& sb, int n, double ds_voxel, const b2_icp_params* params,
+                          bool map_empty, int par, bool front_downsampled) {
     // n is the capacity the kernels are launched for; the live point count sits in *n_dev
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
-    // one scan needs no sort: scratch-hash passes (b2_stream.cu) unless b2_set_scan_path selected the radix path
-    const bool fast = c->scan_path == B2_SCAN_PATH_HASH && stream_applicable(n);
-    if (fast) B2_TRY(stream_begin(c, n));
+    const bool fast = scan_fast(c, n);
+    if (fast) B2_TRY(stream_begin_main(c, n));
+    const int pre_par = front_downsampled ? par : -1;
     if (!map_empty) {
-        const float4* src = scan;
-        const int* ns_dev = n_dev;
+        const float4* src = sb.scan;
+        const int* ns_dev = sb.n_dev;
         if (ds_voxel > 0.0) {
-            B2_WS(c, sdown, float4, WS_SRC_DOWN, sizeof(float4) * (size_t)n);
-            B2_WS(c, cnt, int, WS_COUNTS, sizeof(int) * 4);
-            if (fast) {
-                B2_TRY(stream_downsample(c, scan, n, n_dev, ds_voxel, sdown, cnt));
-            } else {
-                DownsampleOut dso{sdown, nullptr, nullptr, nullptr};
+            if (!front_downsampled) {
+                DownsampleOut dso{sb.sdown, nullptr, nullptr, nullptr};
                 VoxelSortOut vs;
-                B2_TRY(voxel_downsample(c, scan, n, n_dev, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
+                B2_TRY(voxel_downsample(c, sb.scan, n, sb.n_dev, nullptr, 1, ds_voxel, 0, nullptr, nullptr, dso, &vs));
                 // keep the voxel count where later sorts cannot overwrite it
-                B2_CUDA_OK(c, cudaMemcpyAsync(cnt, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+                B2_CUDA_OK(c, cudaMemcpyAsync(sb.cnt, &vs.ctl->nseg, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
             }
-            src = sdown;
-            ns_dev = cnt;
+            src = sb.sdown;
+            ns_dev = sb.cnt;
         }
         GridView g;
         B2_TRY(map_grid_view(c, &g));
         B2_TRY(icp_run(c, src, n, nullptr, ns_dev, 1, g, nullptr, nullptr, pose, to_internal(params), res, nullptr,
                        nullptr, 0, 0));
         // fuse with the registered pose straight from the result record; the pose prior is committed last
-        if (fast) B2_TRY(map_fuse_stream(c, scan, n, n_dev, res->T));
-        else B2_TRY(map_fuse(c, scan, n, n_dev, res->T));
+        if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, res->T, pre_par));
+        else B2_TRY(map_fuse(c, sb.scan, n, sb.n_dev, res->T));
         copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose, c->dev_status);
         B2_LAUNCH_CHECK(c);
         return B2_OK;
     }
-    if (fast) B2_TRY(map_fuse_stream(c, scan, n, n_dev, pose));
-    else B2_TRY(map_fuse(c, scan, n, n_dev, pose));
+    if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, pose, -1));
+    else B2_TRY(map_fuse(c, sb.scan, n, sb.n_dev, pose));
     return B2_OK;
 }
 
-// The step is ~100 small kernels; replaying it as a CUDA graph removes the per-launch CPU cost and
+// Each half is ~10-40 small kernels; replaying it as a CUDA graph removes the per-launch CPU cost and
 // most of the inter-kernel gap.  A graph is keyed by everything baked into its nodes (sizes,
-// parameters, workspace/map addresses); the first call with a new key runs eagerly (it sizes the
-// workspaces), the second captures, later calls replay.
-static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n_dev, double ds_voxel,
-                             const b2_icp_params* params) {
+// parameters, workspace/map addresses, scan path); the first call with a new key runs eagerly (it sizes the
+// workspaces), the second captures, later calls replay.  `body` launches on c->stream.
+static int run_graphed(Context* c, ScanGraph& sg, int n, double ds_voxel, const void* scan,
+                       const b2_icp_params* params, const std::function<int()>& body) {
     static const bool no_graph = getenv("B2_NO_GRAPH") != nullptr;
-    ScanGraph& sg = c->scan_graph;
     const bool same = sg.n == n && sg.ds_voxel == ds_voxel && sg.scan == scan && sg.passes_hint == c->sort_passes_hint &&
                       std::memcmp(&sg.params, params, sizeof(*params)) == 0 && sg.generation == c->ws_generation;
-    if (no_graph) return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
+    if (no_graph) return body();
     if (same && sg.exec) {
         B2_CUDA_OK(c, cudaGraphLaunch(sg.exec, c->stream));
         c->launches += sg.kernel_nodes;
@@ -860,7 +913,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
     if (!same) {  // new shape: eager run, remember the key
         if (sg.exec) cudaGraphExecDestroy(sg.exec);
         sg.exec = nullptr;
-        B2_TRY(slam_body(c, scan, n, n_dev, ds_voxel, params, false));
+        B2_TRY(body());
         sg.n = n; sg.ds_voxel = ds_voxel; sg.scan = scan; sg.params = *params; sg.generation = c->ws_generation;
         sg.passes_hint = c->sort_passes_hint;
         return B2_OK;
@@ -869,7 +922,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
     const unsigned long long launches_before = c->launches;
     B2_CUDA_OK(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     c->capturing = true;
-    int rc = slam_body(c, scan, n, n_dev, ds_voxel, params, false);
+    int rc = body();
     c->capturing = false;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
@@ -879,7 +932,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
         sg.n = -1;  // do not try again with this key until it changes
         c->launches = launches_before;
         if (rc != B2_OK && rc != B2_ERR_CUDA) return rc;
-        return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
+        return body();
     }
     e = cudaGraphInstantiate(&sg.exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -887,7 +940,7 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
         sg.exec = nullptr;
         sg.n = -1;
         c->launches = launches_before;
-        return slam_body(c, scan, n, n_dev, ds_voxel, params, false);
+        return body();
     }
     sg.kernel_nodes = (int)(c->launches - launches_before);
     c->launches = launches_before + sg.kernel_nodes;
@@ -897,79 +950,95 @@ static int slam_body_graphed(Context* c, const float4* scan, int n, const int* n
 
 static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
                           const b2_icp_params* params, b2_icp_result* out, bool map_empty) {
-    // The scan always lands in one fixed device buffer, kernels are launched for a capacity bucket and
-    // read the live point count from device memory: the step's graph is replayed for every scan size
+    // The scan lands in one of two fixed device buffers, kernels are launched for a capacity bucket and
+    // read the live point count from device memory: the step's graphs are replayed for every scan size
     // of the bucket (real scans drop a varying number of invalid pixels).
     const int cap = (n + 8191) / 8192 * 8192;
-    B2_WS(c, scan, float4, WS_SCAN_PTS, sizeof(float4) * (size_t)cap);
-    B2_WS(c, n_dev, int, WS_SCAN_COUNT, sizeof(int) * 4);
-    {   // the live count goes through a pinned ring slot of its own: the copy below is asynchronous and a caller
-        // that passes out == NULL runs many scans ahead of the device
-        const unsigned slot = c->scan_seq % kResultRing;
-        constexpr unsigned kPerBlock = kResultRing / 4;
-        if (slot % kPerBlock == 0) {
-            const int blk = (int)(slot / kPerBlock);
-            // entering block blk: its previous use (kResultRing scans ago) must have run.  Everything up to the
-            // start of the block after it was covered by that block's event.
-            const int guard = (blk + 1) & 3;
-            if (c->block_valid[guard]) B2_CUDA_OK(c, cudaEventSynchronize(c->ev_block[guard]));
-            B2_CUDA_OK(c, cudaEventRecord(c->ev_block[blk], c->stream));
-            c->block_valid[blk] = true;
-        }
-        c->scan_seq++;
-        int* hn = c->count_ring + slot;
-        *hn = n;
-        B2_CUDA_OK(c, cudaMemcpyAsync(n_dev, hn, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    }
-    if (scan_dev) {
-        B2_CUDA_OK(c, cudaMemcpyAsync(scan, scan_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-    } else {
-        // upload on the copy stream into the staging buffer that is not being unpacked: with a caller that
-        // runs ahead (out == NULL) the copy of this scan overlaps the registration of the previous one
-        const int sb = (int)(c->scan_seq & 1u);
-        B2_WS(c, stage0, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)cap);
-        B2_WS(c, stage1, float, WS_STAGE_XYZ2, sizeof(float) * 3 * (size_t)cap);
-        float* stage = sb ? stage1 : stage0;
-        if (c->consumed_valid[sb]) B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[sb], 0));
-        // A pageable source (the ordinary NumPy array a ROS callback holds) is first copied into a pinned ring
-        // slot of the library: the device copy is then truly asynchronous, overlaps the previous scan's
-        // registration, and the caller's array may be released as soon as the call returns.
-        const float* h2d_src = xyz_host;
-        cudaPointerAttributes pa;
-        const bool pageable = cudaPointerGetAttributes(&pa, xyz_host) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
-        cudaGetLastError();
-        if (pageable) {
-            const size_t bytes = sizeof(float) * 3 * (size_t)n;
-            const int hs = (int)(c->host_stage_seq++ % Context::kHostStages);
-            if (c->host_stage_bytes[hs] < bytes) {
-                if (c->host_stage[hs]) {
-                    B2_CUDA_OK(c, cudaEventSynchronize(c->ev_host_stage[hs]));
-                    cudaFreeHost(c->host_stage[hs]);
-                    c->host_stage[hs] = nullptr;
-                }
-                const size_t want = sizeof(float) * 3 * (size_t)cap;
-                B2_CUDA_OK(c, cudaHostAlloc(&c->host_stage[hs], want, cudaHostAllocDefault));
-                c->host_stage_bytes[hs] = want;
-                if (!c->ev_host_stage[hs]) B2_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_host_stage[hs], cudaEventDisableTiming));
-            } else {
-                B2_CUDA_OK(c, cudaEventSynchronize(c->ev_host_stage[hs]));  // its previous upload has run
+    const int par = (int)(c->scan_seq & 1u);
+    ScanBuffers sb;
+    B2_TRY(scan_buffers(c, cap, par, &sb));
+    const bool front_ds = scan_fast(c, cap) && !map_empty && ds_voxel > 0.0;
+    b2_icp_params front_key{};  // (the front half does not depend on the ICP parameters)
+    // ---- front half ------------------------------------------------------------------------------------------
+    {
+        // the buffers of this parity were last read by the main half of the scan before the previous one
+        if (c->consumed_valid[par]) B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[par], 0));
+        {   // the live count goes through a pinned ring slot of its own: the copy below is asynchronous and a caller
+            // that passes out == NULL runs many scans ahead of the device
+            const unsigned slot = c->scan_seq % kResultRing;
+            constexpr unsigned kPerBlock = kResultRing / 4;
+            if (slot % kPerBlock == 0) {
+                const int blk = (int)(slot / kPerBlock);
+                // entering block blk: its previous use (kResultRing scans ago) must have run.  Everything up to the
+                // start of the block after it was covered by that block's event.
+                const int guard = (blk + 1) & 3;
+                if (c->block_valid[guard]) B2_CUDA_OK(c, cudaEventSynchronize(c->ev_block[guard]));
+                B2_CUDA_OK(c, cudaEventRecord(c->ev_block[blk], c->copy_stream));
+                c->block_valid[blk] = true;
             }
-            std::memcpy(c->host_stage[hs], xyz_host, bytes);
-            h2d_src = (const float*)c->host_stage[hs];
-            B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
-            B2_CUDA_OK(c, cudaEventRecord(c->ev_host_stage[hs], c->copy_stream));
-        } else {
-            B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+            c->scan_seq++;
+            int* hn = c->count_ring + slot;
+            *hn = n;
+            B2_CUDA_OK(c, cudaMemcpyAsync(sb.n_dev, hn, sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
         }
-        B2_CUDA_OK(c, cudaEventRecord(c->ev_copied[sb], c->copy_stream));
-        B2_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[sb], 0));
-        pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->stream>>>(stage, n, scan);
-        B2_LAUNCH_CHECK(c);
-        B2_CUDA_OK(c, cudaEventRecord(c->ev_consumed[sb], c->stream));
-        c->consumed_valid[sb] = true;
+        if (scan_dev) {
+            // A device scan may have been produced by a library call on the main stream since the last scan step
+            // (b2_pack_xyz, b2_project_pixels, b2_ingest_pointcloud2 ...): then the front stream has to wait for it.
+            // A scan that was ready before the previous step was submitted needs no such wait and overlaps it.
+            if (c->launches != c->launches_after_scan) {
+                B2_CUDA_OK(c, cudaEventRecord(c->ev_dev_ready, c->stream));
+                B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_dev_ready, 0));
+            }
+            B2_CUDA_OK(c, cudaMemcpyAsync(sb.scan, scan_dev, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToDevice, c->copy_stream));
+        } else {
+            B2_WS(c, stage0, float, WS_STAGE_XYZ, sizeof(float) * 3 * (size_t)cap);
+            B2_WS(c, stage1, float, WS_STAGE_XYZ2, sizeof(float) * 3 * (size_t)cap);
+            float* stage = par ? stage1 : stage0;
+            // A pageable source (the ordinary NumPy array a ROS callback holds) is first copied into a pinned ring
+            // slot of the library: the device copy is then truly asynchronous, overlaps the previous scan's
+            // registration, and the caller's array may be released as soon as the call returns.
+            const float* h2d_src = xyz_host;
+            cudaPointerAttributes pa;
+            const bool pageable = cudaPointerGetAttributes(&pa, xyz_host) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+            cudaGetLastError();
+            const size_t bytes = sizeof(float) * 3 * (size_t)n;
+            if (pageable) {
+                const int hs = (int)(c->host_stage_seq++ % Context::kHostStages);
+                if (c->host_stage_bytes[hs] < bytes) {
+                    if (c->host_stage[hs]) {
+                        B2_CUDA_OK(c, cudaEventSynchronize(c->ev_host_stage[hs]));
+                        cudaFreeHost(c->host_stage[hs]);
+                        c->host_stage[hs] = nullptr;
+                    }
+                    const size_t want = sizeof(float) * 3 * (size_t)cap;
+                    B2_CUDA_OK(c, cudaHostAlloc(&c->host_stage[hs], want, cudaHostAllocDefault));
+                    c->host_stage_bytes[hs] = want;
+                    if (!c->ev_host_stage[hs]) B2_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_host_stage[hs], cudaEventDisableTiming));
+                } else {
+                    B2_CUDA_OK(c, cudaEventSynchronize(c->ev_host_stage[hs]));  // its previous upload has run
+                }
+                std::memcpy(c->host_stage[hs], xyz_host, bytes);
+                h2d_src = (const float*)c->host_stage[hs];
+                B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+                B2_CUDA_OK(c, cudaEventRecord(c->ev_host_stage[hs], c->copy_stream));
+            } else {
+                B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
+            }
+            pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->copy_stream>>>(stage, n, sb.scan);
+            B2_LAUNCH_CHECK(c);
+        }
+        if (front_ds) {
+            StreamSwap swap(c, c->copy_stream);
+            B2_TRY(run_graphed(c, c->front_graph[par], cap, ds_voxel, sb.scan, &front_key,
+                               [&]() { return slam_front_body(c, sb, cap, ds_voxel, par); }));
+        }
+        B2_CUDA_OK(c, cudaEventRecord(c->ev_copied[par], c->copy_stream));
     }
-    if (map_empty) B2_TRY(slam_body(c, scan, cap, n_dev, ds_voxel, params, true));
-    else B2_TRY(slam_body_graphed(c, scan, cap, n_dev, ds_voxel, params));
+    // ---- main half -------------------------------------------------------------------------------------------
+    B2_CUDA_OK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[par], 0));
+    if (map_empty) B2_TRY(slam_main_body(c, sb, cap, ds_voxel, params, true, par, false));
+    else B2_TRY(run_graphed(c, c->main_graph[par], cap, ds_voxel, sb.scan, params,
+                            [&]() { return slam_main_body(c, sb, cap, ds_voxel, params, false, par, front_ds); }));
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
     {   // every scan leaves its result in the pinned ring (asynchronous copy): b2_slam_results reads it later
@@ -980,6 +1049,9 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
         else B2_CUDA_OK(c, cudaMemcpyAsync(rr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
         c->scans_total++;
     }
+    B2_CUDA_OK(c, cudaEventRecord(c->ev_consumed[par], c->stream));
+    c->consumed_valid[par] = true;
+    c->launches_after_scan = c->launches;
     if (out) {
         IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
         if (map_empty) {
@@ -989,7 +1061,7 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
             B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
         }
         int rc = check_status(c);
-        if (rc == B2_ERR_KEY_RANGE && c->sort_passes_hint < 8) {
+        if (rc == B2_ERR_KEY_RANGE && c->sort_passes_hint < 8 && !scan_fast(c, cap)) {
             // the scan's voxel extent needs more radix passes than the captured step launches: nothing was
             // committed (pose and map are gated on the status word), so run the step again with the full
             // budget; the graph is keyed on the budget and is re-captured for the following scans
@@ -997,14 +1069,16 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
             IcpResultDev* rr = (IcpResultDev*)c->result_ring + (int)((c->scans_total - 1) % kResultRing);
             if (map_empty) {
                 map_set_voxels_bound(c, 0);
-                B2_TRY(slam_body(c, scan, cap, n_dev, ds_voxel, params, true));
+                B2_TRY(slam_main_body(c, sb, cap, ds_voxel, params, true, par, false));
                 B2_CUDA_OK(c, cudaMemcpyAsync(hr->T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
                 B2_CUDA_OK(c, cudaMemcpyAsync(rr->T, pose, sizeof(double) * 16, cudaMemcpyDeviceToHost, c->stream));
             } else {
-                B2_TRY(slam_body_graphed(c, scan, cap, n_dev, ds_voxel, params));
+                B2_TRY(run_graphed(c, c->main_graph[par], cap, ds_voxel, sb.scan, params,
+                                   [&]() { return slam_main_body(c, sb, cap, ds_voxel, params, false, par, false); }));
                 B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
                 B2_CUDA_OK(c, cudaMemcpyAsync(rr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
             }
+            B2_CUDA_OK(c, cudaEventRecord(c->ev_consumed[par], c->stream));
             rc = check_status(c);
         }
         if (rc != B2_OK) {

@@ -42,7 +42,7 @@ enum WsSlot : int {
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
     WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_SCAN_COUNT, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D,
-    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_ICP_DENSE, WS_STREAM, WS_STREAM_SLOTS, WS_NUM_SLOTS
+    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_ICP_DENSE, WS_STREAM_PRE0, WS_STREAM_PRE1, WS_STREAM_MAIN, WS_STREAM_SLOTS, WS_SCAN_PTS2, WS_SRC_DOWN2, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu
@@ -75,12 +75,14 @@ struct Context {
     unsigned long long ws_generation = 0;  // bumped whenever a workspace / map buffer is (re)allocated
     bool capturing = false;                // inside stream capture: no allocation, no synchronisation
     unsigned scan_seq = 0;                 // scans submitted (indexes the pinned count ring)
-    ScanGraph scan_graph;
+    ScanGraph front_graph[2], main_graph[2];  // the two halves of the scan step, by scan parity
     // b2_slam_scan with host scans: uploads run on a second stream into two alternating staging buffers, so
     // the copy of scan k+1 overlaps the registration of scan k
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool consumed_valid[2] = {false, false};
+    cudaEvent_t ev_dev_ready = nullptr;            // main -> front: a device scan produced on the main stream is ready
+    unsigned long long launches_after_scan = ~0ull;  // c->launches at the end of the last scan step
     // pageable host scans are staged through a small ring of pinned buffers owned by the library
     static constexpr int kHostStages = 4;
     void* host_stage[kHostStages] = {nullptr, nullptr, nullptr, nullptr};
@@ -443,16 +445,19 @@ int statistical_outlier_mask(Context* c, const float4* pts, int n, int nb_neighb
                              double extent, unsigned char* keep);
 int select_points(Context* c, const float4* pts, int n, const unsigned char* keep, float4* out, int* n_out_dev);
 
-// b2_stream.cu — sort-free voxel passes of the streaming scan step (scratch hash per scan)
+// b2_stream.cu — sort-free voxel passes of the streaming scan step (scratch hash per scan); everything launches on
+// c->stream.  `par` = scan parity: the down-sample of scan k+1 may run (front stream) while scan k is registered.
 bool stream_applicable(int n_max);
-int stream_begin(Context* c, int n_max);
+int stream_begin_pre(Context* c, int n_max, int par);
+int stream_begin_main(Context* c, int n_max);
 int stream_downsample(Context* c, const float4* pts, int n_max, const int* n_dev, double voxel, float4* out_pts,
-                      int* out_count_dev);
+                      int* out_count_dev, int par);
+int stream_propagate_status(Context* c, int n_max, int par);
 // btab != null (brick-major map): the collecting pass also creates the bricks of the scan's voxels
 int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev,
                          const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out,
                          BrickEntry* btab, unsigned bmask, unsigned long long* bkeys, unsigned pool_bricks,
-                         long long* counters);
+                         long long* counters, int pre_par);
 
 // b2_map.cu
 void map_free(Context* c);
@@ -461,7 +466,7 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
 int map_grid_view(Context* c, GridView* g);
 int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev);
 // the same through the sort-free per-scan records of b2_stream.cu (stream_begin() must have run in this step)
-int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev);
+int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int pre_par);
 int map_counts(Context* c, long long* cells, long long* voxels);
 int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, long long max_out, long long* n_out);
 int map_merge_records(Context* c, const int* keys3, const double* sums, int n);

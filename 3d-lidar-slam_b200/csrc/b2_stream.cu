@@ -22,7 +22,8 @@
 //                  The per-scan sums differ from in-order fp64 sums by ~1e-15 relative (far inside the 1e-5
 //                  centroid tolerance); keys and counts are exact.
 //
-// 3 + 3 launches instead of 15 + 13.  One zero-fill clears both tables, the bounding box and the scan state.
+// 3 + 3 launches instead of 15 + 13.  The down-sample half runs on the library's FRONT stream: it depends neither on
+// the map nor on the previous pose, so the down-sample of scan k+1 overlaps the registration of scan k.
 #include "b2_common.cuh"
 
 namespace b2 {
@@ -30,18 +31,30 @@ namespace b2 {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kEmitBlock = 1024;
+// The down-sample kernels run on the front stream NEXT TO the ICP chain of the previous scan, whose one CTA per SM
+// holds 640 x 96 of the SM's 65,536 registers: a CTA of 128 threads x 32 registers is exactly what still fits.  Two of
+// them would keep the next ICP CTA out until one retires, so each asks for 100 KB of (unused) dynamic shared memory:
+// with the ICP CTA's 32 KB at most one fits, two when the SM is otherwise empty.
+constexpr int kFront = 128;
+constexpr int kEmitBlock = kFront;
+constexpr size_t kFrontSmem = 0;
 constexpr double kFixScale = 1099511627776.0;        // 2^40
 constexpr double kFixInv = 1.0 / 1099511627776.0;
 
-// layout of the scratch buffer (one zero-fill per scan):
-//   [StreamHead][agg: kMaxEmitBlocks u32][ds keys | ds sums (3 doubles) | ds cnt | ds first][fuse keys | sums | cnt]
-struct StreamHead {
+// Scratch buffers: one per scan parity for the down-sample, [PreHead][agg: kMaxEmitBlocks u32][keys | sums (3
+// doubles) | cnt | first] — the down-sample of scan k+1 runs on the front stream while scan k is still being
+// registered and its status word must survive until the fusion of ITS scan has read it — and one for the fusion,
+// [MainHead][keys | sums | cnt]; each is cleared by one zero-fill on the stream that uses it.
+struct PreHead {
     unsigned long long bbox[6];  // max over ~order_encode(min) [0..2], max over order_encode(max) [3..5]; 0 = no point
-    SortCtl ctl;                 // fuse: n = nseg = unique voxels of the scan (read by the merge kernels)
-    int pad[4];
+    int status;                  // B2_ERR_* of the down-sample (handed to the sticky status word by the fusion)
+    int pad[3];
 };
-constexpr int kMaxEmitBlocks = 1024;
+struct MainHead {
+    SortCtl ctl;                 // fuse: nseg = unique voxels of the scan (read by the merge kernels)
+    int pad[8];
+};
+constexpr int kMaxEmitBlocks = 2048;
 
 struct ScanTable {
     unsigned long long* keys;  // packed key + 1; 0 = vacant
@@ -63,20 +76,20 @@ __device__ __forceinline__ unsigned table_insert(const ScanTable& t, unsigned lo
     return 0xFFFFFFFFu;
 }
 
-__global__ void __launch_bounds__(kBlock)
-ds_bbox_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max, StreamHead* __restrict__ head) {
+__global__ void __launch_bounds__(kFront, 16)
+ds_bbox_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max, PreHead* __restrict__ head) {
     pdl_enter();
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     bool bad = false;
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    for (int i = blockIdx.x * kFront + threadIdx.x; i < n; i += gridDim.x * kFront) {
         const float4 p = __ldg(pts + i);
         mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
         mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
         bad |= !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
     }
     if (bad) mn[0] = -INFINITY;  // (fmin skips NaN: a point without a voxel opens the box, reported by ds_scatter)
-    __shared__ float smn[kBlock / 32][3], smx[kBlock / 32][3];
+    __shared__ float smn[kFront / 32][3], smx[kFront / 32][3];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -91,7 +104,7 @@ ds_bbox_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, in
     __syncthreads();
     if (threadIdx.x < 3) {
         float a = INFINITY, c = -INFINITY;
-        for (int k = 0; k < kBlock / 32; ++k) { a = fminf(a, smn[k][threadIdx.x]); c = fmaxf(c, smx[k][threadIdx.x]); }
+        for (int k = 0; k < kFront / 32; ++k) { a = fminf(a, smn[k][threadIdx.x]); c = fmaxf(c, smx[k][threadIdx.x]); }
         if (a <= c) {
             atomicMax(&head->bbox[threadIdx.x], ~order_encode((double)a));
             atomicMax(&head->bbox[3 + threadIdx.x], order_encode((double)c));
@@ -100,13 +113,12 @@ ds_bbox_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, in
 }
 
 // A.1 with Open3D's own origin (min_bound - v/2): keys are >= 0.
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kFront, 16)
 ds_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max, double voxel,
-                  const StreamHead* __restrict__ head, ScanTable t, unsigned* __restrict__ slot_of,
-                  int* __restrict__ dev_status) {
+                  PreHead* __restrict__ head, ScanTable t, unsigned* __restrict__ slot_of) {
     pdl_enter();
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
-    const int i = blockIdx.x * kBlock + threadIdx.x;
+    const int i = blockIdx.x * kFront + threadIdx.x;
     if (i >= n) return;
     double origin[3];
     bool ok = true;
@@ -117,8 +129,9 @@ ds_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev,
         // Open3D's voxel index is an int32; the packed key holds 21 bits per axis
         ok = ok && isfinite(mn) && isfinite(mx) && floor(ddiv(dsub(mx, origin[d]), voxel)) < 2097151.0;
     }
+    int* status = &head->status;
     if (!ok) {
-        if (i == 0) atomicCAS(dev_status, 0, B2_ERR_KEY_RANGE);
+        if (i == 0) atomicCAS(status, 0, B2_ERR_KEY_RANGE);
         return;
     }
     const float4 p = __ldg(pts + i);
@@ -127,7 +140,7 @@ ds_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev,
     const unsigned long long kz = (unsigned long long)voxel_coord((double)p.z, origin[2], voxel);
     const unsigned h = table_insert(t, ((kx << 42) | (ky << 21) | kz) + 1ull);
     if (h == 0xFFFFFFFFu) {
-        atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
+        atomicCAS(status, 0, B2_ERR_CAPACITY);
         return;
     }
     double* s = reinterpret_cast<double*>(t.sums) + 3 * (size_t)h;
@@ -140,14 +153,14 @@ ds_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev,
 }
 
 // The first point of every voxel writes the voxel's centroid at its rank among the first points.
-__global__ void __launch_bounds__(kEmitBlock)
+__global__ void __launch_bounds__(kEmitBlock, 16)
 ds_emit_kernel(const int* __restrict__ n_dev, int n_max, ScanTable t, const unsigned* __restrict__ slot_of,
                unsigned* __restrict__ agg, float4* __restrict__ out_pts, int* __restrict__ out_count,
-               const int* __restrict__ dev_status) {
+               const PreHead* __restrict__ head) {
     pdl_enter();
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     const int i = blockIdx.x * kEmitBlock + threadIdx.x;
-    const bool failed = *dev_status != 0;
+    const bool failed = *reinterpret_cast<const volatile int*>(&head->status) != 0;
     unsigned h = 0;
     bool owner = false;
     if (i < n && !failed) {
@@ -161,21 +174,21 @@ ds_emit_kernel(const int* __restrict__ n_dev, int n_max, ScanTable t, const unsi
     if (lane == 0) swarp[w] = __popc(ball);
     __syncthreads();
     if (w == 0) {
-        unsigned v = swarp[lane], incl = v;
+        unsigned v = lane < kEmitBlock / 32 ? swarp[lane] : 0u, incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += u;
         }
-        swarp[lane] = incl - v;  // exclusive warp offsets
+        if (lane < kEmitBlock / 32) swarp[lane] = incl - v;  // exclusive warp offsets
         if (lane == 31) {
             // publish this block's aggregate; the predecessors' aggregates give the block's base (look-back)
             __threadfence();
             atomicExch(&agg[blockIdx.x], (incl << 1) | 1u);
         }
     }
-    // every thread t < blockIdx.x waits for block t's aggregate (all blocks of the grid are co-resident:
-    // at most one block of 1024 threads per SM, launched in index order)
+    // the threads share the wait for the aggregates of the blocks before this one (blocks are dispatched in index
+    // order, so whatever a resident block waits for is resident or has finished)
     unsigned mine = 0;
     for (int b = threadIdx.x; b < (int)blockIdx.x; b += kEmitBlock) {
         unsigned v;
@@ -208,10 +221,17 @@ ds_emit_kernel(const int* __restrict__ n_dev, int n_max, ScanTable t, const unsi
 __global__ void __launch_bounds__(kBlock)
 fuse_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max,
                     const double* __restrict__ T, double ox, double oy, double oz, double voxel, ScanTable t,
-                    int* __restrict__ dev_status) {
+                    const PreHead* __restrict__ pre, int* __restrict__ dev_status) {
     pdl_enter();
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (pre) {  // a failed down-sample of this scan fails the step: nothing of it may reach the map
+        const int ps = pre->status;
+        if (ps != 0) {
+            if (i == 0) atomicCAS(dev_status, 0, ps);
+            return;
+        }
+    }
     if (i >= n || *dev_status != 0) return;
     const float4 p = __ldg(pts + i);
     D3 P{(double)p.x, (double)p.y, (double)p.z};
@@ -249,7 +269,7 @@ fuse_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_de
 // is a separate launch).
 __global__ void __launch_bounds__(kBlock)
 fuse_collect_kernel(ScanTable t, double ox, double oy, double oz, double voxel, int* __restrict__ keys3,
-                    double* __restrict__ sums, StreamHead* __restrict__ head, BrickEntry* __restrict__ btab,
+                    double* __restrict__ sums, MainHead* __restrict__ head, BrickEntry* __restrict__ btab,
                     unsigned bmask, unsigned long long* __restrict__ bkeys, unsigned pool_bricks,
                     long long* __restrict__ counters, int* __restrict__ dev_status) {
     pdl_enter();
@@ -320,69 +340,141 @@ ScanTable table_at(char* base, unsigned cap) {
     return t;
 }
 
-struct StreamBuffers {
-    StreamHead* head;
+struct PreBuffers {   // one per scan parity: [PreHead][agg][table], cleared by one zero-fill
+    PreHead* head;
     unsigned* agg;
-    ScanTable ds, fuse;
+    ScanTable ds;
     size_t bytes;
 };
+struct MainBuffers {  // [MainHead][table], cleared by one zero-fill
+    MainHead* head;
+    ScanTable fuse;
+    size_t bytes;
+};
+constexpr size_t kHeadBytes = 256;
+static_assert(sizeof(PreHead) <= kHeadBytes && sizeof(MainHead) <= kHeadBytes, "heads fit their slots");
 
-int stream_buffers(Context* c, int n_max, StreamBuffers* sb) {
+int pre_buffers(Context* c, int n_max, int par, PreBuffers* pb) {
     const unsigned cap = table_slots(n_max);
-    const size_t head_bytes = (sizeof(StreamHead) + 255) & ~(size_t)255;
     const size_t agg_bytes = sizeof(unsigned) * kMaxEmitBlocks;
-    const size_t total = head_bytes + agg_bytes + 2 * table_bytes(cap);
-    B2_WS(c, raw, char, WS_STREAM, total);
-    sb->head = reinterpret_cast<StreamHead*>(raw);
-    sb->agg = reinterpret_cast<unsigned*>(raw + head_bytes);
-    sb->ds = table_at(raw + head_bytes + agg_bytes, cap);
-    sb->fuse = table_at(raw + head_bytes + agg_bytes + table_bytes(cap), cap);
-    sb->bytes = total;
+    const size_t total = kHeadBytes + agg_bytes + table_bytes(cap);
+    B2_WS(c, raw, char, (par & 1) ? WS_STREAM_PRE1 : WS_STREAM_PRE0, total);
+    pb->head = reinterpret_cast<PreHead*>(raw);
+    pb->agg = reinterpret_cast<unsigned*>(raw + kHeadBytes);
+    pb->ds = table_at(raw + kHeadBytes + agg_bytes, cap);
+    pb->bytes = total;
     return B2_OK;
+}
+
+int main_buffers(Context* c, int n_max, MainBuffers* mb) {
+    const unsigned cap = table_slots(n_max);
+    const size_t total = kHeadBytes + table_bytes(cap);
+    B2_WS(c, raw, char, WS_STREAM_MAIN, total);
+    mb->head = reinterpret_cast<MainHead*>(raw);
+    mb->fuse = table_at(raw + kHeadBytes, cap);
+    mb->bytes = total;
+    return B2_OK;
+}
+
+__global__ void propagate_status_kernel(const PreHead* __restrict__ pre, int* __restrict__ dev_status) {
+    if (pre->status != 0) atomicCAS(dev_status, 0, pre->status);
 }
 
 }  // namespace
 
-bool stream_applicable(int n_max) { return n_max > 0 && div_up(n_max, kEmitBlock) <= kSMs; }
+bool stream_applicable(int n_max) { return n_max > 0 && div_up(n_max, kEmitBlock) <= kMaxEmitBlocks; }
 
-// Clear the scratch state of one scan step (both tables, bounding box, look-back flags): one zero-fill.
-int stream_begin(Context* c, int n_max) {
-    StreamBuffers sb;
-    B2_TRY(stream_buffers(c, n_max, &sb));
-    B2_CUDA_OK(c, cudaMemsetAsync(sb.head, 0, sb.bytes, c->stream));
+namespace {
+// launch of a front-stream kernel: programmatic stream serialisation + the dynamic shared memory that caps the CTAs
+// per SM (see kFrontSmem)
+template <typename... KArgs, typename... Args>
+cudaError_t front_launch(void (*kernel)(KArgs...), dim3 grid, cudaStream_t stream, Args... args) {
+    static const bool off = getenv("B2_NO_PDL") != nullptr;
+    // (once per kernel: this function is instantiated per kernel signature and every signature here is one kernel;
+    // the first launch of a kernel is always an eager one, outside stream capture)
+    static const cudaError_t attr_rc =
+        kFrontSmem > 48 * 1024 ? cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFrontSmem)
+                               : cudaSuccess;
+    if (attr_rc != cudaSuccess) return attr_rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kFront);
+    cfg.dynamicSmemBytes = kFrontSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+}  // namespace
+
+// Clear the down-sample's scratch state (table, bounding box, look-back flags, status) of scan parity `par`.
+int stream_begin_pre(Context* c, int n_max, int par) {
+    PreBuffers pb;
+    B2_TRY(pre_buffers(c, n_max, par, &pb));
+    B2_CUDA_OK(c, cudaMemsetAsync(pb.head, 0, pb.bytes, c->stream));
+    return B2_OK;
+}
+
+// Clear the fusion's scratch state (table, voxel count).
+int stream_begin_main(Context* c, int n_max) {
+    MainBuffers mb;
+    B2_TRY(main_buffers(c, n_max, &mb));
+    B2_CUDA_OK(c, cudaMemsetAsync(mb.head, 0, mb.bytes, c->stream));
     return B2_OK;
 }
 
 // voxel_down_sample(pts, voxel) with Open3D's origin, sort-free (see the header).  out_pts [n_max] float4
-// (w = voxel point count), *out_count_dev = number of voxels.  stream_begin() must have run in this step.
+// (w = voxel point count), *out_count_dev = number of voxels (0 when the pass failed: the reason stays in the
+// parity's status word until the fusion of the same scan — or stream_propagate_status — hands it on).
+// stream_begin_pre(par) must have run.  Launches on c->stream.
 int stream_downsample(Context* c, const float4* pts, int n_max, const int* n_dev, double voxel, float4* out_pts,
-                      int* out_count_dev) {
+                      int* out_count_dev, int par) {
     if (!(voxel > 0.0)) return set_error(c, B2_ERR_INVALID, "voxel size must be > 0 (got %g)", voxel);
-    StreamBuffers sb;
-    B2_TRY(stream_buffers(c, n_max, &sb));
+    PreBuffers sb;
+    B2_TRY(pre_buffers(c, n_max, par, &sb));
+    PreHead* head = sb.head;
     B2_WS(c, slot_of, unsigned, WS_STREAM_SLOTS, sizeof(unsigned) * (size_t)n_max);
-    pdl_launch(ds_bbox_kernel, dim3(min(div_up(n_max, kBlock * 2), kSMs)), dim3(kBlock), c->stream, pts, n_dev, n_max,
-               sb.head);
+    B2_CUDA_OK(c, front_launch(ds_bbox_kernel, dim3(min(div_up(n_max, kFront * 2), 2 * kSMs)), c->stream, pts, n_dev, n_max,
+                               head));
     B2_LAUNCH_CHECK(c);
-    pdl_launch(ds_scatter_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, pts, n_dev, n_max, voxel,
-               (const StreamHead*)sb.head, sb.ds, slot_of, c->dev_status);
+    B2_CUDA_OK(c, front_launch(ds_scatter_kernel, dim3(div_up(n_max, kFront)), c->stream, pts, n_dev, n_max, voxel, head,
+                               sb.ds, slot_of));
     B2_LAUNCH_CHECK(c);
-    pdl_launch(ds_emit_kernel, dim3(div_up(n_max, kEmitBlock)), dim3(kEmitBlock), c->stream, n_dev, n_max, sb.ds,
-               (const unsigned*)slot_of, sb.agg, out_pts, out_count_dev, (const int*)c->dev_status);
+    B2_CUDA_OK(c, front_launch(ds_emit_kernel, dim3(div_up(n_max, kEmitBlock)), c->stream, n_dev, n_max, sb.ds,
+                               (const unsigned*)slot_of, sb.agg, out_pts, out_count_dev, (const PreHead*)head));
+    B2_LAUNCH_CHECK(c);
+    return B2_OK;
+}
+
+// Hand a failed down-sample's reason to the sticky status word (stand-alone use of stream_downsample).
+int stream_propagate_status(Context* c, int n_max, int par) {
+    PreBuffers sb;
+    B2_TRY(pre_buffers(c, n_max, par, &sb));
+    propagate_status_kernel<<<1, 1, 0, c->stream>>>((const PreHead*)sb.head, c->dev_status);
     B2_LAUNCH_CHECK(c);
     return B2_OK;
 }
 
 // The (key, sum, count) records of voxel_down_sample(T * pts, voxel) at an explicit origin, sort-free:
-// keys3 [n_max,3], sums [n_max,4], count in *ctl_out->nseg.  stream_begin() must have run in this step.
+// keys3 [n_max,3], sums [n_max,4], count in *ctl_out->nseg.  stream_begin_main() must have run in this step.
+// pre_par >= 0: the scan's down-sample ran under that parity; its failure fails this pass as well.
 int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev,
                          const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out,
                          BrickEntry* btab, unsigned bmask, unsigned long long* bkeys, unsigned pool_bricks,
-                         long long* counters) {
-    StreamBuffers sb;
-    B2_TRY(stream_buffers(c, n_max, &sb));
+                         long long* counters, int pre_par) {
+    MainBuffers sb;
+    B2_TRY(main_buffers(c, n_max, &sb));
+    const PreHead* pre = nullptr;
+    if (pre_par >= 0) {
+        PreBuffers pb;
+        B2_TRY(pre_buffers(c, n_max, pre_par, &pb));
+        pre = pb.head;
+    }
     pdl_launch(fuse_scatter_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, pts, n_dev, n_max, T_dev,
-               origin[0], origin[1], origin[2], voxel, sb.fuse, c->dev_status);
+               origin[0], origin[1], origin[2], voxel, sb.fuse, pre, c->dev_status);
     B2_LAUNCH_CHECK(c);
     pdl_launch(fuse_collect_kernel, dim3(div_up((long long)sb.fuse.mask + 1, kBlock)), dim3(kBlock), c->stream, sb.fuse,
                origin[0], origin[1], origin[2], voxel, keys3, sums, sb.head, btab, bmask, bkeys, pool_bricks, counters,

@@ -117,7 +117,7 @@ int b2_ingest_pointcloud2(b2_handle h, const void* data, int data_on_host, int n
  * count of the voxel), out_keys_dev int32 [n,3] or NULL, *n_out = voxel count. */
 int b2_voxel_downsample(b2_handle h, const float* pts_dev, int n, double voxel, const double* origin,
                         const double* T, float* out_pts_dev, int* out_keys_dev, int* n_out);
-/* The same down-sample for ONE scan (n <= 151,552 points) without a sort — the pass b2_slam_scan runs in front
+/* The same down-sample for ONE scan (n <= 262,144 points) without a sort — the pass b2_slam_scan runs in front
  * of ICP (icp_processor.py:90): Open3D's origin, centroids bit-identical to b2_voxel_downsample's, emitted in the
  * order of each voxel's first point in the input (pixel order) instead of voxel-key order. */
 int b2_scan_downsample(b2_handle h, const float* pts_dev, int n, double voxel, float* out_pts_dev, int* n_out);
@@ -196,7 +196,10 @@ int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, co
 int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
                  b2_icp_result* out);
 /* Same step for a scan that already lives on the device as float32 [n,4] rows (offline replay of
- * device-resident batches): no upload, otherwise identical. */
+ * device-resident batches): no upload, otherwise identical.  The rows are copied on the library's front stream,
+ * which is ordered after every library call made on this handle so far; a scan written by the CALLER'S OWN kernels
+ * must be complete (or ordered before this call by b2_synchronize / an event wait on the handle's stream plus any
+ * library call) when the call is made. */
 int b2_slam_scan_dev(b2_handle h, const float* scan_xyzw_dev, int n, double ds_voxel, const b2_icp_params* params,
                      b2_icp_result* out);
 /* Deferred read-back for callers that submit scans faster than they need the poses: pass out == NULL to

@@ -92,7 +92,7 @@ def test_scan_path_and_scan_downsample_arguments(raw, b2):
     assert lib.b2_scan_downsample(h, None, 500, 0.02, out.data_ptr(), C.byref(n)) == INVALID
     assert lib.b2_scan_downsample(h, pts.data_ptr(), 500, 0.0, out.data_ptr(), C.byref(n)) == INVALID
     assert lib.b2_scan_downsample(h, pts.data_ptr(), 500, 0.02, out.data_ptr(), None) == INVALID
-    big = 200_000  # beyond the single-scan limit of the look-back scan (one 1024-point block per SM)
+    big = 300_000  # beyond the single-scan limit of the look-back scan (2048 blocks of 128 points)
     assert lib.b2_scan_downsample(h, pts.data_ptr(), big, 0.02, out.data_ptr(), C.byref(n)) == INVALID
     assert "b2_voxel_downsample" in _err(lib, h)
     assert lib.b2_scan_downsample(h, pts.data_ptr(), 0, 0.02, out.data_ptr(), C.byref(n)) == 0 and n.value == 0
