@@ -852,6 +852,7 @@ static bool scan_fast(Context* c, int n) { return c->scan_path == B2_SCAN_PATH_H
 // front half after the scan sits in scan[par] (launches on c->stream = the front stream while it runs)
 static int slam_front_body(Context* c, const ScanBuffers& sb, int n, double ds_voxel, int par) {
     B2_TRY(stream_begin_pre(c, n, par));
+    B2_TRY(stream_begin_main(c, n, par));  // (the fusion's zero-fill, taken off the main stream's critical path)
     B2_TRY(stream_downsample(c, sb.scan, n, sb.n_dev, ds_voxel, sb.sdown, sb.cnt, par));
     return B2_OK;
 }
@@ -863,7 +864,7 @@ static int slam_main_body(Context* c, const ScanBuffers& sb, int n, double ds_vo
     double* pose = map_pose_dev(c);
     IcpResultDev* res = map_result_dev(c);
     const bool fast = scan_fast(c, n);
-    if (fast) B2_TRY(stream_begin_main(c, n));
+    if (fast && !front_downsampled) B2_TRY(stream_begin_main(c, n, par));
     const int pre_par = front_downsampled ? par : -1;
     if (!map_empty) {
         const float4* src = sb.scan;
@@ -884,13 +885,13 @@ static int slam_main_body(Context* c, const ScanBuffers& sb, int n, double ds_vo
         B2_TRY(icp_run(c, src, n, nullptr, ns_dev, 1, g, nullptr, nullptr, pose, to_internal(params), res, nullptr,
                        nullptr, 0, 0));
         // fuse with the registered pose straight from the result record; the pose prior is committed last
-        if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, res->T, pre_par));
+        if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, res->T, par, pre_par));
         else B2_TRY(map_fuse(c, sb.scan, n, sb.n_dev, res->T));
         copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose, c->dev_status);
         B2_LAUNCH_CHECK(c);
         return B2_OK;
     }
-    if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, pose, -1));
+    if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, pose, par, -1));
     else B2_TRY(map_fuse(c, sb.scan, n, sb.n_dev, pose));
     return B2_OK;
 }
@@ -963,6 +964,9 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
     {
         // the buffers of this parity were last read by the main half of the scan before the previous one
         if (c->consumed_valid[par]) B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[par], 0));
+        static const bool no_overlap = getenv("B2_NO_OVERLAP") != nullptr;  // A/B switch: front half after the previous scan
+        if (no_overlap && c->consumed_valid[par ^ 1])
+            B2_CUDA_OK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[par ^ 1], 0));
         {   // the live count goes through a pinned ring slot of its own: the copy below is asynchronous and a caller
             // that passes out == NULL runs many scans ahead of the device
             const unsigned slot = c->scan_seq % kResultRing;

@@ -42,7 +42,7 @@ enum WsSlot : int {
     WS_SRC_DOWN, WS_SRC_KEYS, WS_STAGE_XYZ, WS_SCAN_PTS, WS_NORMALS_TMP, WS_GRID2_ENTRIES, WS_GRID2_PTS,
     WS_GRID2_META, WS_MISC, WS_EXPORT_KEYS, WS_EXPORT_PTS, WS_TGT_DOWN, WS_TGT_KEYS, WS_TGT_NORMALS,
     WS_CORR, WS_FILTER_MEAN, WS_FILTER_PART, WS_FILTER_KEEP, WS_SCAN_COUNT, WS_BATCH_A, WS_BATCH_B, WS_BATCH_C, WS_BATCH_D,
-    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_ICP_DENSE, WS_STREAM_PRE0, WS_STREAM_PRE1, WS_STREAM_MAIN, WS_STREAM_SLOTS, WS_SCAN_PTS2, WS_SRC_DOWN2, WS_NUM_SLOTS
+    WS_INGEST_RAW, WS_INGEST_TMP, WS_INGEST_KEEP, WS_STAGE_XYZ2, WS_ICP_DENSE, WS_STREAM_PRE0, WS_STREAM_PRE1, WS_STREAM_MAIN0, WS_STREAM_MAIN1, WS_STREAM_SLOTS, WS_SCAN_PTS2, WS_SRC_DOWN2, WS_NUM_SLOTS
 };
 
 struct MapState;  // b2_map.cu
@@ -449,7 +449,7 @@ int select_points(Context* c, const float4* pts, int n, const unsigned char* kee
 // c->stream.  `par` = scan parity: the down-sample of scan k+1 may run (front stream) while scan k is registered.
 bool stream_applicable(int n_max);
 int stream_begin_pre(Context* c, int n_max, int par);
-int stream_begin_main(Context* c, int n_max);
+int stream_begin_main(Context* c, int n_max, int par);
 int stream_downsample(Context* c, const float4* pts, int n_max, const int* n_dev, double voxel, float4* out_pts,
                       int* out_count_dev, int par);
 int stream_propagate_status(Context* c, int n_max, int par);
@@ -457,7 +457,7 @@ int stream_propagate_status(Context* c, int n_max, int par);
 int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev,
                          const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out,
                          BrickEntry* btab, unsigned bmask, unsigned long long* bkeys, unsigned pool_bricks,
-                         long long* counters, int pre_par);
+                         long long* counters, int par, int pre_par);
 
 // b2_map.cu
 void map_free(Context* c);
@@ -466,7 +466,8 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
 int map_grid_view(Context* c, GridView* g);
 int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev);
 // the same through the sort-free per-scan records of b2_stream.cu (stream_begin() must have run in this step)
-int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int pre_par);
+int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int par,
+                    int pre_par);
 int map_counts(Context* c, long long* cells, long long* voxels);
 int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, long long max_out, long long* n_out);
 int map_merge_records(Context* c, const int* keys3, const double* sums, int n);

@@ -488,7 +488,8 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
     return B2_OK;
 }
 
-int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int pre_par) {
+int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int par,
+                    int pre_par) {
     MapState* m = c->map;
     if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
     if (n_max <= 0) return B2_OK;
@@ -497,14 +498,14 @@ int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, 
     SortCtl* ctl = nullptr;
     if (m->brick == 1) {  // the collecting pass creates the bricks: only the merge is left
         B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl, m->btab,
-                                    m->capacity - 1, m->bkeys, m->pool_bricks, m->counters, pre_par));
+                                    m->capacity - 1, m->bkeys, m->pool_bricks, m->counters, par, pre_par));
         pdl_launch(brick_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
                    (const double*)dsums, (const SortCtl*)ctl, (const BrickEntry*)m->btab, m->capacity - 1, m->cent, m->acc,
                    m->counters, m->max_voxels, c->dev_status);
         B2_LAUNCH_CHECK(c);
     } else {
         B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl, nullptr, 0,
-                                    nullptr, 0, nullptr, pre_par));
+                                    nullptr, 0, nullptr, par, pre_par));
         B2_TRY(merge_launch(c, m, dkeys, dsums, ctl, n_max));
     }
     m->host_voxels_bound += n_max;

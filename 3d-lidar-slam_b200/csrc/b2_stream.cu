@@ -52,7 +52,8 @@ struct PreHead {
 };
 struct MainHead {
     SortCtl ctl;                 // fuse: nseg = unique voxels of the scan (read by the merge kernels)
-    int pad[8];
+    int nlist;                   // occupied table slots so far (the thread that creates a slot appends it to the list)
+    int pad[7];
 };
 constexpr int kMaxEmitBlocks = 2048;
 
@@ -64,13 +65,16 @@ struct ScanTable {
     unsigned mask;
 };
 
-__device__ __forceinline__ unsigned table_insert(const ScanTable& t, unsigned long long key) {
+__device__ __forceinline__ unsigned table_insert(const ScanTable& t, unsigned long long key, bool* created = nullptr) {
     unsigned h = (unsigned)hash64(key) & t.mask;
 #pragma unroll 1
     for (unsigned probe = 0; probe <= t.mask; ++probe) {
         unsigned long long cur = t.keys[h];
         if (cur == 0ull) cur = atomicCAS(&t.keys[h], 0ull, key);
-        if (cur == 0ull || cur == key) return h;
+        if (cur == 0ull || cur == key) {
+            if (created) *created = cur == 0ull;
+            return h;
+        }
         h = (h + 1) & t.mask;
     }
     return 0xFFFFFFFFu;
@@ -221,7 +225,8 @@ ds_emit_kernel(const int* __restrict__ n_dev, int n_max, ScanTable t, const unsi
 __global__ void __launch_bounds__(kBlock)
 fuse_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_dev, int n_max,
                     const double* __restrict__ T, double ox, double oy, double oz, double voxel, ScanTable t,
-                    const PreHead* __restrict__ pre, int* __restrict__ dev_status) {
+                    MainHead* __restrict__ head, unsigned* __restrict__ list, const PreHead* __restrict__ pre,
+                    int* __restrict__ dev_status) {
     pdl_enter();
     const int n = n_dev ? min(*n_dev, n_max) : n_max;
     const int i = blockIdx.x * kBlock + threadIdx.x;
@@ -251,11 +256,13 @@ fuse_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_de
         double fr = q[d] - fl;  // exact (Sterbenz), in [0, 1)
         f[d] = (long long)(fr * kFixScale);
     }
-    const unsigned h = table_insert(t, map_cell_key(k[0], k[1], k[2]) + 1ull);
+    bool created = false;
+    const unsigned h = table_insert(t, map_cell_key(k[0], k[1], k[2]) + 1ull, &created);
     if (h == 0xFFFFFFFFu) {
         atomicCAS(dev_status, 0, B2_ERR_CAPACITY);
         return;
     }
+    if (created) list[atomicAdd(&head->nlist, 1)] = h;  // (a few thousand per scan: the scan's unique voxels)
     unsigned long long* s = t.sums + 3 * (size_t)h;
     atomicAdd(s, (unsigned long long)f[0]);
     atomicAdd(s + 1, (unsigned long long)f[1]);
@@ -263,27 +270,22 @@ fuse_scatter_kernel(const float4* __restrict__ pts, const int* __restrict__ n_de
     atomicAdd(&t.cnt[h], 1u);
 }
 
-// Occupied slots -> (voxel key, (sum x, sum y, sum z, count)) records for the map's merge kernel.  When the map is
-// brick-major (btab != null) the thread also makes sure the voxel's brick exists (the work of brick_ensure_kernel:
-// the winner of the key CAS takes the next pool brick and publishes its index; nobody waits for it here, the merge
-// is a separate launch).
+// Occupied slots (listed by the scatter pass) -> (voxel key, (sum x, sum y, sum z, count)) records for the map's
+// merge kernel.  When the map is brick-major (btab != null) the thread also makes sure the voxel's brick exists (the
+// work of brick_ensure_kernel: the winner of the key CAS takes the next pool brick and publishes its index; nobody
+// waits for it here, the merge is a separate launch).
 __global__ void __launch_bounds__(kBlock)
 fuse_collect_kernel(ScanTable t, double ox, double oy, double oz, double voxel, int* __restrict__ keys3,
-                    double* __restrict__ sums, MainHead* __restrict__ head, BrickEntry* __restrict__ btab,
-                    unsigned bmask, unsigned long long* __restrict__ bkeys, unsigned pool_bricks,
-                    long long* __restrict__ counters, int* __restrict__ dev_status) {
+                    double* __restrict__ sums, MainHead* __restrict__ head, const unsigned* __restrict__ list,
+                    BrickEntry* __restrict__ btab, unsigned bmask, unsigned long long* __restrict__ bkeys,
+                    unsigned pool_bricks, long long* __restrict__ counters, int* __restrict__ dev_status) {
     pdl_enter();
-    const unsigned h = blockIdx.x * kBlock + threadIdx.x;
-    const unsigned long long key = (h <= t.mask && *dev_status == 0) ? t.keys[h] : 0ull;
-    const bool occ = key != 0ull;
-    const unsigned ball = __ballot_sync(0xffffffffu, occ);
-    if (ball == 0u) return;
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&head->ctl.nseg, __popc(ball));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (!occ) return;
-    const int j = base + __popc(ball & ((1u << lane) - 1u));
+    const int j = blockIdx.x * kBlock + threadIdx.x;
+    const int n = *dev_status == 0 ? head->nlist : 0;
+    if (j == 0) head->ctl.nseg = n;
+    if (j >= n) return;
+    const unsigned h = list[j];
+    const unsigned long long key = t.keys[h];
     const unsigned long long k = key - 1ull;
     const int kx = (int)((k >> 42) & 0x1FFFFF) - (1 << 20);
     const int ky = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
@@ -346,10 +348,11 @@ struct PreBuffers {   // one per scan parity: [PreHead][agg][table], cleared by 
     ScanTable ds;
     size_t bytes;
 };
-struct MainBuffers {  // [MainHead][table], cleared by one zero-fill
+struct MainBuffers {  // one per scan parity: [MainHead][table] cleared by one zero-fill, then the slot list
     MainHead* head;
     ScanTable fuse;
-    size_t bytes;
+    unsigned* list;   // [n_max] occupied slots in creation order
+    size_t bytes;     // of the zero-filled part
 };
 constexpr size_t kHeadBytes = 256;
 static_assert(sizeof(PreHead) <= kHeadBytes && sizeof(MainHead) <= kHeadBytes, "heads fit their slots");
@@ -366,13 +369,14 @@ int pre_buffers(Context* c, int n_max, int par, PreBuffers* pb) {
     return B2_OK;
 }
 
-int main_buffers(Context* c, int n_max, MainBuffers* mb) {
+int main_buffers(Context* c, int n_max, int par, MainBuffers* mb) {
     const unsigned cap = table_slots(n_max);
-    const size_t total = kHeadBytes + table_bytes(cap);
-    B2_WS(c, raw, char, WS_STREAM_MAIN, total);
+    const size_t fill = kHeadBytes + table_bytes(cap);
+    B2_WS(c, raw, char, (par & 1) ? WS_STREAM_MAIN1 : WS_STREAM_MAIN0, fill + sizeof(unsigned) * (size_t)n_max);
     mb->head = reinterpret_cast<MainHead*>(raw);
     mb->fuse = table_at(raw + kHeadBytes, cap);
-    mb->bytes = total;
+    mb->list = reinterpret_cast<unsigned*>(raw + fill);
+    mb->bytes = fill;
     return B2_OK;
 }
 
@@ -418,10 +422,11 @@ int stream_begin_pre(Context* c, int n_max, int par) {
     return B2_OK;
 }
 
-// Clear the fusion's scratch state (table, voxel count).
-int stream_begin_main(Context* c, int n_max) {
+// Clear the fusion's scratch state (table, voxel count) of scan parity `par` — on c->stream: the front half does it
+// for the scans whose down-sample it runs (off the critical path), the main half otherwise.
+int stream_begin_main(Context* c, int n_max, int par) {
     MainBuffers mb;
-    B2_TRY(main_buffers(c, n_max, &mb));
+    B2_TRY(main_buffers(c, n_max, par, &mb));
     B2_CUDA_OK(c, cudaMemsetAsync(mb.head, 0, mb.bytes, c->stream));
     return B2_OK;
 }
@@ -464,9 +469,9 @@ int stream_propagate_status(Context* c, int n_max, int par) {
 int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev,
                          const double* origin, double voxel, int* keys3, double* sums, SortCtl** ctl_out,
                          BrickEntry* btab, unsigned bmask, unsigned long long* bkeys, unsigned pool_bricks,
-                         long long* counters, int pre_par) {
+                         long long* counters, int par, int pre_par) {
     MainBuffers sb;
-    B2_TRY(main_buffers(c, n_max, &sb));
+    B2_TRY(main_buffers(c, n_max, par, &sb));
     const PreHead* pre = nullptr;
     if (pre_par >= 0) {
         PreBuffers pb;
@@ -474,11 +479,11 @@ int stream_voxel_records(Context* c, const float4* pts, int n_max, const int* n_
         pre = pb.head;
     }
     pdl_launch(fuse_scatter_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, pts, n_dev, n_max, T_dev,
-               origin[0], origin[1], origin[2], voxel, sb.fuse, pre, c->dev_status);
+               origin[0], origin[1], origin[2], voxel, sb.fuse, sb.head, sb.list, pre, c->dev_status);
     B2_LAUNCH_CHECK(c);
-    pdl_launch(fuse_collect_kernel, dim3(div_up((long long)sb.fuse.mask + 1, kBlock)), dim3(kBlock), c->stream, sb.fuse,
-               origin[0], origin[1], origin[2], voxel, keys3, sums, sb.head, btab, bmask, bkeys, pool_bricks, counters,
-               c->dev_status);
+    pdl_launch(fuse_collect_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, sb.fuse,
+               origin[0], origin[1], origin[2], voxel, keys3, sums, sb.head, (const unsigned*)sb.list, btab, bmask, bkeys,
+               pool_bricks, counters, c->dev_status);
     B2_LAUNCH_CHECK(c);
     *ctl_out = &sb.head->ctl;
     return B2_OK;
