@@ -885,13 +885,16 @@ static int slam_main_body(Context* c, const ScanBuffers& sb, int n, double ds_vo
         B2_TRY(icp_run(c, src, n, nullptr, ns_dev, 1, g, nullptr, nullptr, pose, to_internal(params), res, nullptr,
                        nullptr, 0, 0));
         // fuse with the registered pose straight from the result record; the pose prior is committed last
-        if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, res->T, par, pre_par));
+        bool committed = false;
+        if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, res->T, par, pre_par, res, &committed));
         else B2_TRY(map_fuse(c, sb.scan, n, sb.n_dev, res->T));
-        copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose, c->dev_status);
-        B2_LAUNCH_CHECK(c);
+        if (!committed) {
+            copy_pose_kernel<<<1, 32, 0, c->stream>>>(res, pose, c->dev_status);
+            B2_LAUNCH_CHECK(c);
+        }
         return B2_OK;
     }
-    if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, pose, par, -1));
+    if (fast) B2_TRY(map_fuse_stream(c, sb.scan, n, sb.n_dev, pose, par, -1, nullptr, nullptr));
     else B2_TRY(map_fuse(c, sb.scan, n, sb.n_dev, pose));
     return B2_OK;
 }

@@ -466,8 +466,9 @@ int map_init(Context* c, double voxel, const double* origin, double max_corr, lo
 int map_grid_view(Context* c, GridView* g);
 int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev);
 // the same through the sort-free per-scan records of b2_stream.cu (stream_begin() must have run in this step)
+// commit_res != null: the merge kernel of a brick-major map also copies commit_res->T to the pose prior (*committed)
 int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int par,
-                    int pre_par);
+                    int pre_par, const IcpResultDev* commit_res, bool* committed);
 int map_counts(Context* c, long long* cells, long long* voxels);
 int map_export(Context* c, float4* out_pts, int* out_keys, double* out_sums, long long max_out, long long* n_out);
 int map_merge_records(Context* c, const int* keys3, const double* sums, int n);

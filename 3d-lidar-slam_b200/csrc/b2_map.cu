@@ -219,9 +219,12 @@ __global__ void __launch_bounds__(kBlock)
 brick_merge_kernel(const int* __restrict__ keys3, const double* __restrict__ sums, const SortCtl* __restrict__ ctl,
                    const BrickEntry* __restrict__ tab, unsigned mask, float4* __restrict__ cells,
                    double* __restrict__ acc, long long* __restrict__ counters, unsigned long long max_voxels,
-                   int* __restrict__ dev_status) {
+                   int* __restrict__ dev_status, const IcpResultDev* __restrict__ commit_res,
+                   double* __restrict__ commit_pose) {
     pdl_enter();
     const int j = blockIdx.x * kBlock + threadIdx.x;
+    // scan step: the registered pose becomes the prior of the next scan together with the merge (same gate)
+    if (commit_res && j < 16 && *dev_status == 0) commit_pose[j] = commit_res->T[j];
     if (j >= ctl->nseg || *dev_status != 0) return;
     unsigned long long bkey;
     unsigned local;
@@ -461,7 +464,7 @@ static int merge_launch(Context* c, MapState* m, const int* keys3, const double*
         B2_LAUNCH_CHECK(c);
         pdl_launch(brick_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums, ctl,
                    (const BrickEntry*)m->btab, m->capacity - 1, m->cent, m->acc, m->counters, m->max_voxels,
-                   c->dev_status);
+                   c->dev_status, (const IcpResultDev*)nullptr, (double*)nullptr);
     } else {
         const unsigned long long max_cells = (unsigned long long)(0.7 * (double)m->capacity);
         pdl_launch(map_merge_kernel, dim3(div_up(n, kBlock)), dim3(kBlock), c->stream, keys3, sums, ctl, m->entries,
@@ -489,7 +492,7 @@ int map_fuse(Context* c, const float4* pts, int n_max, const int* n_dev, const d
 }
 
 int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, const double* T_dev, int par,
-                    int pre_par) {
+                    int pre_par, const IcpResultDev* commit_res, bool* committed) {
     MapState* m = c->map;
     if (!m) return set_error(c, B2_ERR_STATE, "map not initialised (call b2_map_init)");
     if (n_max <= 0) return B2_OK;
@@ -501,8 +504,9 @@ int map_fuse_stream(Context* c, const float4* pts, int n_max, const int* n_dev, 
                                     m->capacity - 1, m->bkeys, m->pool_bricks, m->counters, par, pre_par));
         pdl_launch(brick_merge_kernel, dim3(div_up(n_max, kBlock)), dim3(kBlock), c->stream, (const int*)dkeys,
                    (const double*)dsums, (const SortCtl*)ctl, (const BrickEntry*)m->btab, m->capacity - 1, m->cent, m->acc,
-                   m->counters, m->max_voxels, c->dev_status);
+                   m->counters, m->max_voxels, c->dev_status, commit_res, m->pose);
         B2_LAUNCH_CHECK(c);
+        if (committed) *committed = commit_res != nullptr;
     } else {
         B2_TRY(stream_voxel_records(c, pts, n_max, n_dev, T_dev, m->origin, m->voxel, dkeys, dsums, &ctl, nullptr, 0,
                                     nullptr, 0, nullptr, par, pre_par));
