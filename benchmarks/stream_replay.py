@@ -38,6 +38,8 @@ def main():
     ap.add_argument("--capacity", type=int, default=1 << 23)
     ap.add_argument("--preload-length", type=float, default=0.0, help="metres of corridor surface fused before frame 0")
     ap.add_argument("--reference-frames", type=int, default=0)
+    ap.add_argument("--reference-maintenance", default="full", choices=["full", "voxel", "off"],
+                    help="do_stuff variant of the mode='reference' side run (icp_processor.py:121-148)")
     ap.add_argument("--deferred", action="store_true", help="also time the replay with the poses read every 64 frames")
     ap.add_argument("--loop", action="store_true",
                     help="also replay the wire-format records through the queue + plugin.ProcessLoop (row f4)")
@@ -66,7 +68,8 @@ def main():
     def make_proc(mode):
         return set_algorithm("b200_icp", cfg, DataTransfer(), multiprocessing.Event(), mode=mode,
                              voxel_size=0.02, max_correspondence_distance=0.05, map_voxel=args.map_voxel,
-                             map_origin=origin, max_iteration=args.max_iteration, map_capacity_cells=args.capacity)
+                             map_origin=origin, max_iteration=args.max_iteration, map_capacity_cells=args.capacity,
+                             maintenance=args.reference_maintenance)
 
     inv0 = np.linalg.inv(poses[0])
 
@@ -171,6 +174,7 @@ def main():
             dt = time.perf_counter() - t0
             m = p.global_map
             out[mode] = {"frames": k, "seconds": round(dt, 2), "map_points": int(len(m)),
+                         "maintenance": args.reference_maintenance if mode == "reference" else "none",
                          "drift_m": {"max": round(max(e), 4), "final": round(e[-1], 4)},
                          "mean_fitness": round(float(np.mean(f)), 4), "mean_iterations": round(float(np.mean(it)), 2)}
             p.engine.close()
