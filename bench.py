@@ -27,6 +27,8 @@ Keys of the JSON line (rank 0 prints exactly one):
                    per-scan rebuild (oracle.cpp: ResidentMap).
   batched_pairs    config 5: 8192 independent scan pairs split over the ranks (STRONG scaling), one NCCL
                    all-gather of the 152-byte result records inside the timed region.
+  partial_map_merge   N > 1: every rank's ~2.1 M-voxel map exported as (key, sum, count) records, all-gathered over
+                   NCCL and merged count-weighted; the merged map is checked to be identical on all ranks.
   streaming        config 4 (benchmarks/stream_replay.py in a child process): 1000-frame replay through the plugin,
                    resumed on an ~8 M-voxel map (map tables far beyond L2); sustained scans/s, first vs last 100
                    frames, map size over time, drift.
@@ -384,6 +386,8 @@ def run_ours(args):
 
     if not args.no_batched and args.pairs_total > 0:
         line["batched_pairs"] = run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2batch)
+    if world > 1 and not args.no_batched:
+        line["partial_map_merge"] = run_map_merge(eng, world, device, barrier, max_over_ranks, b2batch)
     if rank == 0 and world == 1 and args.streaming > 0:
         line["streaming"] = run_streaming(args.streaming)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -557,6 +561,32 @@ def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2b
                                    "roofline numerator"}
     del S4, T4
     return out
+
+
+def run_map_merge(eng, world, device, barrier, max_over_ranks, b2batch):
+    """The partial-map gather + merge of SURVEY.md 8(e) on real maps (N > 1; runs last, it replaces the rank's map):
+    every rank exports its resident map (~2.1 M voxels, a different scene per rank in the same volume) as
+    (key, sum xyz, count) records, NCCL all-gathers them, and merges all ranks' records count-weighted.  The merged
+    map must be the same on every rank: checked through the voxel count and the sum of all point counts."""
+    import torch
+    import torch.distributed as dist
+
+    before = eng.map_size()
+    barrier()
+    t0 = time.perf_counter()
+    merged = b2batch.merge_partial_maps(eng)
+    eng.synchronize()
+    barrier()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    _, sums = eng.map_export_records()
+    points = float(sums[:, 3].sum().item())
+    t = torch.tensor([float(merged), -float(merged), points, -points], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    same = bool(t[0].item() == -t[1].item() and t[2].item() == -t[3].item())
+    return {"ms": round(ms, 2), "voxels_per_rank_before": int(before), "voxels_merged": int(merged),
+            "points_merged": int(points), "identical_on_all_ranks": same,
+            "bytes_gathered_per_rank": int(before) * (12 + 32) * world,
+            "collective": "all_gather of the record counts + two padded all_gathers (int32 keys, fp64 sums), NCCL"}
 
 
 def run_streaming(frames: int):
