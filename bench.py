@@ -422,7 +422,21 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
     eng.synchronize()
     launches = (eng.launch_count() - l0) / reps   # step kernels + the one-thread init kernel of a registration
     n_launch = launches - 1
-    us_per_launch = ev0.elapsed_time(ev1) * 1e3 / (reps * n_launch)
+    us_eager = ev0.elapsed_time(ev1) * 1e3 / (reps * n_launch)
+    # the same kernel where the timed region runs it: inside the graph-replayed scan step.  Two budgets with the
+    # convergence test disabled (every launch active); the difference of the step times is (30 - 6) ICP launches.
+    def scan_step_us(iters, n=24):
+        prm_i = b2.make_params(MAX_CORR, iters, rel_fitness=0.0, rel_rmse=0.0)
+        for rep in range(2):   # first pass: eager + capture per parity, second pass: timed replays
+            eng.set_pose(poses[0])
+            with torch.cuda.stream(eng.stream):
+                ev0.record()
+                for k in range(n):
+                    eng.slam_scan_dev(dev_scans[k], DS_VOXEL, prm_i)
+                ev1.record()
+            eng.synchronize()
+        return ev0.elapsed_time(ev1) * 1e3 / n
+    us_per_launch = (scan_step_us(30) - scan_step_us(6)) / 24.0
     cand = eng.stencil_candidates(sd, init)
     bytes_8d = 16 * ns + 16 * cand + 136
     bytes_ext = bytes_8d + 27 * 16 * ns + 136 * 148
@@ -432,10 +446,14 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
             "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "frac_extended": round(bytes_ext / (us_per_launch * 1e-6) / 1e9 / peak, 4),
             "traffic": ICP_DENSE_TRAFFIC_DEFAULT if ICP_DENSE_TRAFFIC is None else ICP_DENSE_TRAFFIC,
-            "us_per_launch": round(us_per_launch, 3), "launches_per_registration": round(n_launch, 1),
+            "us_per_launch": round(us_per_launch, 3), "us_per_launch_eager_chain": round(us_eager, 3),
+            "launches_per_registration": round(n_launch, 1),
             "queries": int(ns), "candidates": int(cand),
             "algorithmic_bytes_per_launch": int(bytes_8d), "algorithmic_bytes_extended": int(bytes_ext),
-            "note": "us_per_launch = duration of a chain of launches / launches, i.e. it includes the launch-to-launch "
+            "note": "us_per_launch = (scan step with a 30-iteration budget - scan step with a 6-iteration budget) / 24, "
+                    "convergence test disabled, graph-replayed as in the timed region (CUDA events on the library's "
+                    "stream); us_per_launch_eager_chain = a registration launched eagerly / its launches.  Either way "
+                    "the figure is the duration of a chain of launches / launches, i.e. it includes the launch-to-launch "
                     "dependency (fold of the previous partials + SE(3) solve + broadcast), which is most of it: a step "
                     "is a chain of dependent latencies, not a bandwidth problem (measured DRAM traffic per launch is "
                     "below the algorithmic bytes: the stencils of neighbouring queries overlap in L1/L2)"}
