@@ -243,3 +243,38 @@ def test_hash_scan_path_on_a_slab_map_matches_the_resident_cpu_map(b2):
     np.testing.assert_allclose(c[:, :3], oc, rtol=1e-5, atol=1e-5)
     cpu_map.close()
     eng.close()
+
+
+@pytest.mark.parametrize("path", ["hash", "sorted"])
+def test_scan_step_edge_sizes_and_no_downsample(b2, path):
+    """Tiny and ragged scans through the scan step (1, 2, 31, 33, 1025 points; ds_voxel = 0: the scan is the ICP
+    source as it is), eager / captured / replayed: both scan paths keep the map equal to the oracle's voxel
+    down-sample of everything fused (keys and counts exact), and a one-point scan is a legal scan."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(21, length=8.0)
+    pose = synth.corridor_trajectory(scene, 1, seed=21)[0]
+    full = synth.render_scan(scene, pose, seed=5).numpy()
+    origin = np.array([-20.0, -20.0, -20.0])
+    eng = b2.Engine(0)
+    eng.map_init(0.05, origin, 0.05, 1 << 18)
+    eng.set_scan_path(path)
+    prm = b2.make_params(0.05, 10)
+    fused = []
+    # the first scan is the map; the others (subsets of it) register against its voxel centroids
+    for n, ds in ((len(full), 0.02), (1, 0.02), (2, 0.0), (31, 0.02), (33, 0.0), (1025, 0.02), (1025, 0.02), (1025, 0.02)):
+        s = full[:: max(1, len(full) // n)][:n].copy()
+        eng.set_pose(np.eye(4))              # every scan starts from the identity prior
+        res = eng.slam_scan(s, ds, prm)
+        fused.append((s, res.matrix()))
+        if len(fused) > 1:
+            assert np.isfinite(res.matrix()).all() and 0.0 <= res.fitness <= 1.0 and res.iterations <= 10
+            if n > 2:    # (one or two correspondences leave the rotation undetermined: the SVD fall-back's choice)
+                assert np.abs(res.matrix() - np.eye(4)).max() < 0.05   # a subset of the map: the pose stays put
+    _, keys = eng.map_export()
+    cent, _ = eng.map_export(want_keys=False)
+    world = np.concatenate([orc.transform(f64(s), T) for s, T in fused])
+    _, ok, on = orc.voxel_downsample(world, 0.05, origin=origin)
+    np.testing.assert_array_equal(keys.cpu().numpy(), ok)
+    np.testing.assert_array_equal(cent.cpu().numpy()[:, 3].copy().view(np.int32), on)
+    eng.close()
