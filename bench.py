@@ -460,7 +460,7 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
 
 
 # traffic of the dense kernel from the committed ncu capture (bytes per launch); see profiles/README.md
-ICP_DENSE_TRAFFIC_DEFAULT = 781_000
+ICP_DENSE_TRAFFIC_DEFAULT = 773_600
 
 
 def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2batch):
