@@ -26,7 +26,7 @@ EXPORTS = [
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
     "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results", "b2_icp_batch_p2l",
-    "b2_estimate_normals_batch", "b2_map_export_records", "b2_map_merge_records", "b2_set_scan_path", "b2_scan_downsample",
+    "b2_estimate_normals_batch", "b2_map_export_records", "b2_map_merge_records", "b2_set_scan_path", "b2_scan_downsample", "b2_slam_scan_records",
 ]
 
 
@@ -94,6 +94,7 @@ def load():
         "b2_map_icp": [vp, vp, i32, pd, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan_dev": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
+        "b2_slam_scan_records": [vp, vp, i32, f64, f64, f64, f64, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_results": [vp, i32, C.POINTER(IcpResult)],
         "b2_map_stencil_candidates": [vp, vp, i32, pd, C.POINTER(i64)],
         "b2_radius_outlier_mask": [vp, vp, i32, i32, f64, vp, C.POINTER(i32)],
@@ -425,6 +426,19 @@ class Engine:
         res = IcpResult() if want_result else None
         self._check(self.lib.b2_slam_scan(self.h, xyz_host.ctypes.data, xyz_host.shape[0], float(ds_voxel),
                                           C.byref(params), C.byref(res) if want_result else None))
+        return res
+
+    def slam_scan_records(self, records_host: np.ndarray, fx, fy, cx, cy, numpy2: bool, ds_voxel: float,
+                          params: IcpParams, want_result: bool = True):
+        """The scan step fed with the wire-format records (x_px, y_px, depth) float32 [n,3] of one depth image:
+        the projection (generic_point_cloud_processor.py:93-108) runs on the device as part of the upload."""
+        if records_host.dtype != np.float32 or records_host.ndim != 2 or records_host.shape[1] != 3 or \
+                not records_host.flags["C_CONTIGUOUS"]:
+            raise ValueError("expected a C-contiguous float32 [n,3] host array of (x_px, y_px, depth) records")
+        res = IcpResult() if want_result else None
+        self._check(self.lib.b2_slam_scan_records(self.h, records_host.ctypes.data, records_host.shape[0], float(fx),
+                                                  float(fy), float(cx), float(cy), int(bool(numpy2)), float(ds_voxel),
+                                                  C.byref(params), C.byref(res) if want_result else None))
         return res
 
     def slam_scan_dev(self, scan4, ds_voxel: float, params: IcpParams, want_result: bool = False):

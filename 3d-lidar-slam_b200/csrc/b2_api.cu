@@ -952,8 +952,10 @@ static int run_graphed(Context* c, ScanGraph& sg, int n, double ds_voxel, const 
     return B2_OK;
 }
 
+// proj != null: xyz_host holds (x_px, y_px, depth) records and proj = {fx, fy, cx, cy, numpy2 != 0}: the front half
+// back-projects them (generic_point_cloud_processor.py:93-108) while it packs.
 static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
-                          const b2_icp_params* params, b2_icp_result* out, bool map_empty) {
+                          const b2_icp_params* params, b2_icp_result* out, bool map_empty, const double* proj) {
     // The scan lands in one of two fixed device buffers, kernels are launched for a capacity bucket and
     // read the live point count from device memory: the step's graphs are replayed for every scan size
     // of the bucket (real scans drop a varying number of invalid pixels).
@@ -1031,7 +1033,11 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
             } else {
                 B2_CUDA_OK(c, cudaMemcpyAsync(stage, h2d_src, bytes, cudaMemcpyHostToDevice, c->copy_stream));
             }
-            pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->copy_stream>>>(stage, n, sb.scan);
+            if (proj)
+                project_kernel<<<div_up(n, kBlock), kBlock, 0, c->copy_stream>>>(stage, n, proj[0], proj[1], proj[2],
+                                                                               proj[3], proj[4] != 0.0, sb.scan);
+            else
+                pack_xyz_kernel<<<div_up(n, kBlock), kBlock, 0, c->copy_stream>>>(stage, n, sb.scan);
             B2_LAUNCH_CHECK(c);
         }
         if (front_ds) {
@@ -1098,7 +1104,7 @@ static int slam_scan_impl(Context* c, const float* xyz_host, const float4* scan_
 }
 
 static int slam_scan_entry(Context* c, const float* xyz_host, const float4* scan_dev, int n, double ds_voxel,
-                           const b2_icp_params* params, b2_icp_result* out) {
+                           const b2_icp_params* params, b2_icp_result* out, const double* proj = nullptr) {
     B2_TRY(check_params(c, params));
     if (n <= 0 || (!xyz_host && !scan_dev)) return set_error(c, B2_ERR_INVALID, "b2_slam_scan: empty scan");
     if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "the resident map holds no normals: point-to-point only");
@@ -1109,13 +1115,22 @@ static int slam_scan_entry(Context* c, const float* xyz_host, const float4* scan
                          params->max_correspondence_distance, map_max_corr(c));
     // "first scan becomes the map" (icp_processor.py:53-56): decided on the host from the fuse history
     const bool map_empty = map_is_empty_host(c);
-    return slam_scan_impl(c, xyz_host, scan_dev, n, ds_voxel, params, out, map_empty);
+    return slam_scan_impl(c, xyz_host, scan_dev, n, ds_voxel, params, out, map_empty, proj);
 }
 
 int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
                  b2_icp_result* out) {
     CTX(h);
     return slam_scan_entry(c, xyz_host, nullptr, n, ds_voxel, params, out);
+}
+
+int b2_slam_scan_records(b2_handle h, const float* records_host, int n, double fx, double fy, double cx, double cy,
+                         int numpy2_semantics, double ds_voxel, const b2_icp_params* params, b2_icp_result* out) {
+    CTX(h);
+    if (!(fx != 0.0) || !(fy != 0.0) || !std::isfinite(fx) || !std::isfinite(fy) || !std::isfinite(cx) || !std::isfinite(cy))
+        return set_error(c, B2_ERR_INVALID, "b2_slam_scan_records: intrinsics must be finite, fx and fy non-zero");
+    const double proj[5] = {fx, fy, cx, cy, numpy2_semantics ? 1.0 : 0.0};
+    return slam_scan_entry(c, records_host, nullptr, n, ds_voxel, params, out, proj);
 }
 
 int b2_slam_results(b2_handle h, int count, b2_icp_result* out) {

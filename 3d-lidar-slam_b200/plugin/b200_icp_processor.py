@@ -191,9 +191,10 @@ class B200ICPProcessor(ProcessPointClouds):
 
     def process(self) -> None:
         """ProcessPointClouds.process (generic_point_cloud_processor.py:111-126) with the projection fused
-        into the upload: the (x_px, y_px, depth) records go to the device as they are and
-        ``b2_project_pixels`` back-projects them there, so the 49k-iteration Python loop of
-        the reference — and any host-side array of metric points — disappears from the per-scan path."""
+        into the upload: the (x_px, y_px, depth) records go to the device as they are and the front half of the scan
+        step back-projects them there (``b2_slam_scan_records``; ``b2_project_pixels`` +
+        ``b2_slam_scan_dev`` in reference mode), so the 49k-iteration Python loop of the reference — and any host-side
+        array of metric points — disappears from the per-scan path."""
         self.process_records(self.data_transfer.pixel_depth_map_queue.get())
 
     def process_records(self, scan, defer_result: bool = False) -> None:
@@ -224,6 +225,12 @@ class B200ICPProcessor(ProcessPointClouds):
             self.logger.info(f"pcs processed so far: {self.point_clouds_in_map}")
             rec = np.ascontiguousarray(_records_to_array(scan), dtype=np.float32)
             del scan
+            if self._mode == "resident":
+                # one call: upload, projection, down-sample (front stream) -> ICP -> fuse (main stream)
+                self._map_cache = None
+                self._construct_resident(None, records=rec)
+                self.point_clouds_in_map += 1
+                return
             pts4 = self._engine.project_pixels(rec, self.fx, self.fy, self.cx, self.cy, numpy2=self._numpy2)
             self._register_device_scan(pts4)
 
@@ -273,7 +280,7 @@ class B200ICPProcessor(ProcessPointClouds):
         super().reset()
 
     # -- resident mode --------------------------------------------------------
-    def _construct_resident(self, pts, pts4=None) -> None:
+    def _construct_resident(self, pts, pts4=None, records=None) -> None:
         eng = self._engine
         if not self._resident_ready:
             eng.map_init(self._map_voxel, self._map_origin, self._max_corr, self._map_capacity)
@@ -282,7 +289,10 @@ class B200ICPProcessor(ProcessPointClouds):
         # enqueue only: upload, down-sample, ICP seeded with the pose kept on the device, fuse.  The pose comes
         # back when somebody reads previous_transformation / last_result / global_map (or MAX_PENDING is reached);
         # a pageable `pts` has been copied into the library's pinned ring when the call returns
-        if pts4 is not None:
+        if records is not None:
+            eng.slam_scan_records(records, self.fx, self.fy, self.cx, self.cy, self._numpy2, self._voxel, self._params,
+                                  want_result=False)
+        elif pts4 is not None:
             eng.slam_scan_dev(pts4, self._voxel, self._params, want_result=False)
         else:
             eng.slam_scan(pts, self._voxel, self._params, want_result=False)

@@ -189,15 +189,20 @@ def preload_map(engine, scene, device):
     return engine.map_size()
 
 
-def make_scans(scene, n_scans: int, device, seed: int, start_x: float = START_X):
-    """Consecutive scans along a smooth trajectory (<= ~2.5 cm / 1 deg per frame) + their true poses."""
+def make_scans(scene, n_scans: int, device, seed: int, start_x: float = START_X, want_records: bool = False):
+    """Consecutive scans along a smooth trajectory (<= ~2.5 cm / 1 deg per frame) + their true poses
+    (+ the wire-format (x_px, y_px, depth) records the scans were projected from)."""
     from lidar_slam_b200 import synth
 
     poses = synth.corridor_trajectory(scene, n_scans, start_x=start_x, step=0.02, seed=seed)
-    scans = [synth.render_scan(scene, p, seed=seed * 100003 + k, device=device).cpu().numpy()
-             for k, p in enumerate(poses)]
+    scans, records = [], []
+    for k, p in enumerate(poses):
+        rec = synth.scan_records(synth.render_depth(scene, p, seed=seed * 100003 + k, device=device))
+        scans.append(synth.project_records(rec).cpu().numpy())
+        if want_records:
+            records.append(rec.cpu().numpy())
     assert all(len(s) == SCAN_POINTS for s in scans), "every pixel of the synthetic scans must be valid"
-    return scans, poses
+    return (scans, poses, records) if want_records else (scans, poses)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -246,7 +251,7 @@ def run_ours(args):
     # 400 MB of device-resident / 300 MB of host inputs, > the 126 MB L2), so no step finds its
     # scans or its part of the map warm in L2 from the step before
     n_seg = max(1, min(8, args.warmup + args.steps))
-    scans, poses = make_scans(scene, S * n_seg, device, seed=rank + 1)
+    scans, poses, records = make_scans(scene, S * n_seg, device, seed=rank + 1, want_records=True)
     prm = b2.make_params(MAX_CORR, MAX_ITER)
 
     # device-resident copies (for `value`), pageable host arrays (plugin e2e), pinned copies (C-ABI e2e)
@@ -280,6 +285,16 @@ def run_ours(args):
             if per_scan_wait:
                 proc.previous_transformation[-1]
         return proc.last_result, proc.previous_transformation[-1], poses[b + S - 1]
+
+    def step_process():
+        """ProcessPointClouds.process minus the queue (generic_point_cloud_processor.py:111-126): the wire-format
+        (x_px, y_px, depth) records of every depth image in, projection on the device as part of the upload."""
+        b = (step_no[2] % n_seg) * S
+        step_no[2] += 1
+        proc.set_pose_prior(poses[b])
+        for k in range(b, b + S):
+            proc.process_records(records[k])
+        return proc.previous_transformation[-1]
 
     def step_cabi(per_scan_sync=False):
         """The bare C-ABI call (b2_slam_scan) with pinned host scans; results collected once per step
@@ -333,6 +348,14 @@ def run_ours(args):
     eng.synchronize()
     barrier()
     plugin_sync = world * S * max(1, args.steps // 2) / max_over_ranks(time.perf_counter() - t0)
+    step_process()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_process()
+    eng.synchronize()
+    barrier()
+    process_value = world * S * args.steps / max_over_ranks(time.perf_counter() - t0)
 
     # ---- the bare C-ABI with pinned scans: deferred results, then a host wait after every scan
     for _ in range(max(1, args.warmup // 2)):
@@ -372,6 +395,10 @@ def run_ours(args):
                         "(H2D of every scan inside); the poses of the step's S scans are read back on the host at the "
                         "end of every step (previous_transformation)",
                 "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h_per_step,
+                "process_records_value": round(process_value, 2),
+                "process_records_note": "B200ICPProcessor.process_records(records): ProcessPointClouds.process minus the "
+                                        "queue — (x_px, y_px, depth) records in, projection fused into the upload "
+                                        "(b2_slam_scan_records), poses read once per step",
                 "plugin_per_scan_wait_value": round(plugin_sync, 2),
                 "plugin_per_scan_wait_note": "the same calls with previous_transformation[-1] read after EVERY scan "
                                              "(a live node that needs each pose before it submits the next scan)",

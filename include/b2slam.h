@@ -195,6 +195,12 @@ int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, co
  * library first, so the caller's buffer may be released as soon as the call returns). */
 int b2_slam_scan(b2_handle h, const float* xyz_host, int n, double ds_voxel, const b2_icp_params* params,
                  b2_icp_result* out);
+/* ProcessPointClouds.process (generic_point_cloud_processor.py:111-126) in one call: the same step fed with the
+ * wire-format records (x_px, y_px, depth_m) float32 [n,3] of one depth image; the pixel -> metric projection of
+ * b2_project_pixels (generic_point_cloud_processor.py:93-108; numpy2_semantics as there) runs on the device as
+ * part of the upload, on the library's front stream, so it overlaps the registration of the previous scan. */
+int b2_slam_scan_records(b2_handle h, const float* records_host, int n, double fx, double fy, double cx, double cy,
+                         int numpy2_semantics, double ds_voxel, const b2_icp_params* params, b2_icp_result* out);
 /* Same step for a scan that already lives on the device as float32 [n,4] rows (offline replay of
  * device-resident batches): no upload, otherwise identical.  The rows are copied on the library's front stream,
  * which is ordered after every library call made on this handle so far; a scan written by the CALLER'S OWN kernels

@@ -284,3 +284,29 @@ def test_deferred_errors_surface_at_the_read_and_leave_the_processor_usable():
     proc.construct_global_map(scans[2]); proc.point_clouds_in_map += 1
     assert len(proc.previous_transformation) == 3 and proc.last_result.fitness > 0.9
     proc.engine.close()
+
+
+def test_process_records_fuses_projection_into_the_scan_step():
+    """process_records (the body of ProcessPointClouds.process) feeds the wire-format records straight to
+    b2_slam_scan_records; the result must equal projecting on the host (generic_point_cloud_processor.py:93-108,
+    the NumPy regime of this interpreter) and calling construct_global_map, bit for bit."""
+    from lidar_slam_b200 import synth
+
+    scene = synth.make_corridor_scene(9, length=10.0)
+    poses = synth.corridor_trajectory(scene, 6, seed=9, step=0.02)
+    recs = [synth.scan_records(synth.render_depth(scene, p, seed=80 + k), keep_prob=0.9, seed=k).numpy()
+            for k, p in enumerate(poses)]
+    a, _ = _processor(mode="resident", max_iteration=30, map_capacity_cells=1 << 20)
+    b, _ = _processor(mode="resident", max_iteration=30, map_capacity_cells=1 << 20)
+    for r in recs:
+        a.process_records(r)
+        b.construct_global_map(b.project_pixel_to_3d(r))
+        b.point_clouds_in_map += 1
+    assert a.point_clouds_in_map == b.point_clouds_in_map
+    ta, tb = list(a.previous_transformation), list(b.previous_transformation)
+    assert len(ta) == len(tb) == len(recs)
+    for x, y in zip(ta, tb):
+        np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(a.global_map, b.global_map)
+    a.engine.close()
+    b.engine.close()
