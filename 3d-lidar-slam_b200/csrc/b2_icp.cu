@@ -452,6 +452,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
             static unsigned mis[64];
             cudaMemcpyFromSymbol(h, g_dense_ts, sizeof(h));
             cudaMemcpyFromSymbol(mis, g_dense_mis, sizeof(mis));
+            fprintf(stderr, "[b2 dense] queries on the full path per launch:");
+            for (int jj = 0; jj < 64 && jj < launches; ++jj) fprintf(stderr, " %u", mis[jj]);
+            fprintf(stderr, "\n");
             const char* names[12] = {"entry", "waited", "folded", "solved", "searched", "exit", "w0:arrived", "w0:spec-issued", "w0:T-seen", "w0:cell", "w0:reloaded", "w0:finished"};
             for (int jj = 2; jj < 8 && jj < launches; ++jj) {
                 unsigned long long t0 = ~0ull;
@@ -498,10 +501,16 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
 int debug_dense_stamps(unsigned long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, g_dense_ts, sizeof(unsigned long long) * 64 * 148 * 16) == cudaSuccess ? 0 : -2;
 }
+int debug_dense_full_path(unsigned* out_host) {  // [64 launches]: queries that took the full path; cleared by the read
+    if (cudaMemcpyFromSymbol(out_host, g_dense_mis, sizeof(unsigned) * 64) != cudaSuccess) return -2;
+    static const unsigned zeros[64] = {0};
+    return cudaMemcpyToSymbol(g_dense_mis, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -2;
+}
 #endif
 
 }  // namespace b2
 
 #ifdef B2_TAIL_TIMING
 extern "C" int b2_debug_dense_stamps(unsigned long long* out_host) { return b2::debug_dense_stamps(out_host); }
+extern "C" int b2_debug_dense_full_path(unsigned* out_host64) { return b2::debug_dense_full_path(out_host64); }
 #endif

@@ -170,15 +170,6 @@ __device__ __forceinline__ void dense_axis(const double* __restrict__ row, float
     ca = voxel_coord(Pa, origin, cell);
 }
 
-// The same with a cell predicted by the speculative pass: [lo, hi) are the bounds of cell `cs` along this axis, a
-// nanometre inside them the IEEE division of voxel_coord cannot give anything else, so it is skipped.
-__device__ __forceinline__ void dense_axis_checked(const double* __restrict__ row, double px, double py, double pz,
-                                                   double origin, double cell, double lo, double hi, int cs,
-                                                   double& Pa, int& ca) {
-    Pa = dadd(dadd(dadd(dmul(row[0], px), dmul(row[1], py)), dmul(row[2], pz)), row[3]);
-    ca = (Pa > lo && Pa < hi) ? cs : voxel_coord(Pa, origin, cell);
-}
-
 // Fetch the nine cells of z-plane nz = cz + g - 1 around (cx, cy): four brick probes issued together, then nine
 // direct loads.  No warp-collective operation inside (callable under divergence).
 __device__ __forceinline__ void dense_load_plane(const DenseArgs& a, int cx, int cy, int cz, int g, bool live,
@@ -232,16 +223,76 @@ __device__ __forceinline__ void dense_load_plane(const DenseArgs& a, int cx, int
     }
 }
 
-// Nearest neighbour of the group's query among the fetched cells + its contribution to the sums.
-// Warp-collective (all 32 lanes enter; `valid` is uniform over a group; g = lane's z-plane 0..2, lead = the
-// group's first lane; lanes 30 / 31 come in with g >= 3, valid == false and empty cells).
-__device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* __restrict__ sPivot, double cellw,
-                                             double Px, double Py, double Pz, const PlaneCells& pc, bool valid, int q,
-                                             int g, int lead, double (&acc)[6]) {
+// What survives the barrier from the SPECULATIVE float32 screening (done with T_{j-1} in the shadow of the solve):
+// the lane's two nearest cells and a lower bound for the distance of every cell that was not kept.
+struct SpecKept {
+    float x1, y1, z1, x2, y2, z2;  // centroids of the nearest / second-nearest cell of this lane's z-plane
+    unsigned pos1, pos2;           // their positions in the brick pool
+    int c12;                       // stencil cell numbers 9 * ix + 3 * iy of the two (c1 | c2 << 8; 0xff: none)
+    float s2, s3;                  // sqrt(d~) (1 - 4e-6) - 2 e_abs of the second-nearest / of the third: with the
+                                   // query's motion subtracted, lower bounds of their exact distances under T_j
+    float e_abs;                   // per-coordinate float32 error bound of the screening
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {  // (relative error 2^-23: inside every margin below)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float dense_e_abs(float Pxf, float Pyf, float Pzf, double cellw) {
+    return (fmaxf(fmaxf(fabsf(Pxf), fabsf(Pyf)), fabsf(Pzf)) + 4.0f * (float)cellw + 1e-3f) * 1.2e-7f;
+}
+
+// The three smallest of the lane's nine float32 squared distances by a min / max insertion network on integer keys
+// (distance bits with the low four mantissa bits replaced by the cell's index k: non-negative floats order like
+// integers; the truncation only LOWERS a distance by <= 2^-19 relative, which the bounds below allow for), then
+// the two winners are re-read from L1 (their lines were fetched a moment ago) instead of being carried through
+// the network.
+__device__ __forceinline__ void dense_screen_top2(const DenseArgs& a, const PlaneCells& pc, float Pxf, float Pyf, float Pzf,
+                                                  double cellw, SpecKept& kp) {
+    int ka = 0x7fffffff, kb = 0x7fffffff, kc = 0x7fffffff;  // smallest, second, third key
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        const float fx = Pxf - pc.t[k].x, fy = Pyf - pc.t[k].y, fz = Pzf - pc.t[k].z;
+        float d = fx * fx + fy * fy + fz * fz;
+        if (__float_as_int(pc.t[k].w) == 0) d = INFINITY;
+        const int key = (__float_as_int(d) & ~15) | k;
+        kc = min(kc, max(kb, key));
+        kb = min(kb, max(ka, key));
+        ka = min(ka, key);
+    }
+    const bool has1 = ka < 0x7f800000, has2 = kb < 0x7f800000;
+    const int k1 = ka & 15, k2 = kb & 15;
+    unsigned p1 = 0u, p2 = 0u;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        if (k == k1) p1 = pc.pos[k];
+        if (k == k2) p2 = pc.pos[k];
+    }
+    float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1;
+    if (has1) t1 = __ldg(a.cells + p1);
+    if (has2) t2 = __ldg(a.cells + p2);
+    kp.x1 = t1.x; kp.y1 = t1.y; kp.z1 = t1.z; kp.pos1 = p1;
+    kp.x2 = t2.x; kp.y2 = t2.y; kp.z2 = t2.z; kp.pos2 = p2;
+    const int c1 = has1 ? 9 * (k1 / 3) + 3 * (k1 % 3) : 0xff, c2 = has2 ? 9 * (k2 / 3) + 3 * (k2 % 3) : 0xff;
+    kp.c12 = c1 | (c2 << 8);
+    kp.e_abs = dense_e_abs(Pxf, Pyf, Pzf, cellw);
+    const float d2 = __int_as_float(kb & ~15), d3 = __int_as_float(kc & ~15);  // (INFINITY stays INFINITY)
+    kp.s2 = sqrt_approx(d2) * 0.999996f - 2.0f * kp.e_abs;
+    kp.s3 = sqrt_approx(d3) * 0.999996f - 2.0f * kp.e_abs;
+}
+
+// One lane's nearest cell among the nine of a freshly fetched z-plane (the full path): float32 screening, then the
+// contenders in exact fp64.  Warp-collective (all 32 lanes enter; lanes 30 / 31 and lanes of groups that do not take
+// part come in with empty planes).
+__device__ __forceinline__ void dense_lane_best(double cellw, double Px, double Py, double Pz, const PlaneCells& pc,
+                                                int g, int lead, double& best, int& best_c, unsigned& best_pos,
+                                                float& bx, float& by, float& bz) {
     // ---- float32 screening of this lane's nine cells: best and second-best squared distance ------------------
     const float Pxf = (float)Px, Pyf = (float)Py, Pzf = (float)Pz;
     float bf = INFINITY, sf = INFINITY;
-    float bx = 0.f, by = 0.f, bz = 0.f;
+    bx = by = bz = 0.f;
     unsigned bpos = 0;
     int bc = 0;
 #pragma unroll
@@ -265,11 +316,11 @@ __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* _
     // arithmetic).  Every candidate's d2_f32 >= d2* - M where d2* is the true minimum, so a candidate with
     // d2_f32 > gmin + 2M has d2 > d2* and cannot be the nearest neighbour; only the contenders (normally one per
     // group) are evaluated in fp64, in the strict order of the oracle.
-    double best = INFINITY;
-    int best_c = 0x7fffffff;
-    unsigned best_pos = 0;
+    best = INFINITY;
+    best_c = 0x7fffffff;
+    best_pos = 0;
     if (gmin < INFINITY) {
-        const float e_abs = (fmaxf(fmaxf(fabsf(Pxf), fabsf(Pyf)), fabsf(Pzf)) + 4.0f * (float)cellw + 1e-3f) * 1.2e-7f;
+        const float e_abs = dense_e_abs(Pxf, Pyf, Pzf, cellw);
         const float M = 3.5f * e_abs * sqrtf(gmin) + 3.0f * e_abs * e_abs + 1e-6f * gmin;
         const float thr = (gmin + 2.0f * M) * 1.000002f + 1e-30f;
         if (bf <= thr) {
@@ -292,10 +343,18 @@ __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* _
             }
         }
     }
-    // ---- arg-min over the group: (d2, stencil cell) lexicographic ------------------------------------------
-    // Normally exactly one lane of the group holds a contender: its values are the group's (one ballot, no
-    // comparison of doubles across lanes); otherwise (near-ties across z-planes, or no candidate at all) every
-    // lane reads the three lanes' (d2, cell) and keeps the lexicographic minimum.
+}
+
+// Arg-min over the group's three lanes + the correspondence's contribution to the sums.
+// Warp-collective (all 32 lanes enter; `valid` is uniform over a group; g = lane's z-plane 0..2, lead = the
+// group's first lane; lanes 30 / 31 come in with g >= 3, valid == false and best == INFINITY).
+__device__ __forceinline__ void dense_group_tail(const DenseArgs& a, const double* __restrict__ sPivot, double Px,
+                                                 double Py, double Pz, double best, int best_c, unsigned best_pos,
+                                                 float bx, float by, float bz, bool valid, int q, int g, int lead,
+                                                 double* __restrict__ colp, bool first) {
+    // (d2, stencil cell) lexicographic.  Normally exactly one lane of the group holds a contender: its values are
+    // the group's (one ballot, no comparison of doubles across lanes); otherwise (near-ties across z-planes, or no
+    // candidate at all) every lane reads the three lanes' (d2, cell) and keeps the lexicographic minimum.
     const unsigned has = (__ballot_sync(kFull, best < INFINITY) >> lead) & 7u;
     double gbest;
     int gc;
@@ -330,17 +389,31 @@ __device__ __forceinline__ void dense_finish(const DenseArgs& a, const double* _
     const int wl = lead + (found ? gc % 3 : 0);
     float4 Q;
     Q.x = __shfl_sync(kFull, bx, wl); Q.y = __shfl_sync(kFull, by, wl); Q.z = __shfl_sync(kFull, bz, wl);
-    if (!found || g >= kDenseLanes) return;
+    if (g >= kDenseLanes) return;
     // ---- the 17 terms, spread over the three lanes: lane g holds axis g of q (q_g, q_g p^T) and p_g; lane 0 also
-    // the squared distance, lane 1 the count ----------------------------------------------------------------------
-    const double px = Px - sPivot[0], py = Py - sPivot[1], pz = Pz - sPivot[2];
-    const double qa = (double)(g == 0 ? Q.x : (g == 1 ? Q.y : Q.z)) - sPivot[g];
-    acc[0] += qa;
-    acc[1] += qa * px;
-    acc[2] += qa * py;
-    acc[3] += qa * pz;
-    acc[4] += g == 0 ? px : (g == 1 ? py : pz);
-    acc[5] += g == 0 ? gbest : (g == 1 ? 1.0 : 0.0);
+    // the squared distance, lane 1 the count; they go straight to the group's shared-memory column (rows by lane
+    // role; the first round stores, a later round — sources beyond 190 queries per CTA — adds) ------------------
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
+    if (found) {
+        const double px = Px - sPivot[0], py = Py - sPivot[1], pz = Pz - sPivot[2];
+        const double qa = (double)(g == 0 ? Q.x : (g == 1 ? Q.y : Q.z)) - sPivot[g];
+        t0 = qa; t1 = qa * px; t2 = qa * py; t3 = qa * pz;
+        t4 = g == 0 ? px : (g == 1 ? py : pz);
+        t5 = g == 0 ? gbest : (g == 1 ? 1.0 : 0.0);
+    } else if (!first) {
+        return;
+    }
+    double* r0 = colp + (3 + g) * kDenseCols;        // q_g
+    double* r1 = colp + (6 + 3 * g) * kDenseCols;    // q_g p^T (three rows)
+    double* r4 = colp + g * kDenseCols;              // p_g
+    double* r5 = colp + (15 + g) * kDenseCols;       // d2 (lane 0) / count (lane 1)
+    if (first) {
+        *r0 = t0; r1[0] = t1; r1[kDenseCols] = t2; r1[2 * kDenseCols] = t3; *r4 = t4;
+        if (g < 2) *r5 = t5;
+    } else {
+        *r0 += t0; r1[0] += t1; r1[kDenseCols] += t2; r1[2 * kDenseCols] += t3; *r4 += t4;
+        if (g < 2) *r5 += t5;
+    }
 }
 
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -358,7 +431,6 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     constexpr int NT = 17;
     constexpr int kParts = kDenseSearchThreads / 32;  // 20
     __shared__ DenseState sDS;
-    __shared__ GridMeta sMeta;
     __shared__ double sAccL[NT][kDenseCols];
     __shared__ double sRed[kParts][kTerms];
     static_assert(sizeof(DenseState) % 8 == 0 && sizeof(GridMeta) % 8 == 0, "copied as 8-byte words");
@@ -384,7 +456,8 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     const bool has_query = col < share && g < kDenseLanes;
     const int q_first = blockIdx.x * share + col;  // this group's query of the first round
     // everything that does not depend on the previous launch: grid metadata, this group's query point
-    const GridMeta meta = *metas;
+    const double m_cell = __ldg(&metas->cell);                              // voxel edge (= cell edge: brick == 1)
+    const double m_org = __ldg(&metas->origin[lane < 30 ? lane % 3 : 0]);   // this lane's axis of the map origin
     float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!control && has_query && q_first < ns) p_first = __ldg(src + q_first);  // (one address per group)
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -465,31 +538,32 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         B2_DTS(6);
         B2_DTS_MAX(14);
 
-        // (c) speculative fetch for the first round's query with T_{j-1}
-        PlaneCells pc;
+        // (c) speculative fetch AND float32 screening for the first round's query with T_{j-1}: what crosses the
+        // barrier is the lane's two nearest cells + a bound for the others (SpecKept), not the nine cells
+        SpecKept kp;
         const int warp_q0 = q_first - grp;
         const bool valid0 = q_first < ns && has_query;
-        const double pdx = (double)p_first.x, pdy = (double)p_first.y, pdz = (double)p_first.z;
         double lo = 1.0, hi = 0.0;  // bounds of the predicted cell along this lane's axis (empty: nothing predicted)
-        int cs = 0;
+        double Pa_old = 0.0;        // this lane's axis of T_{j-1} p
+        bool spec_live;
         {
-            double Pa = 0.0;
+            PlaneCells pc;
+            int cs = 0;
             if (g < 3) {
-                dense_axis(Trow, p_first, meta.origin[g], meta.cell, Pa, cs);
-                lo = dadd(dadd(meta.origin[g], dmul((double)cs, meta.cell)), 1e-9);
-                hi = dsub(dadd(dadd(meta.origin[g], dmul((double)cs, meta.cell)), meta.cell), 1e-9);
+                dense_axis(Trow, p_first, m_org, m_cell, Pa_old, cs);
+                lo = dadd(dadd(m_org, dmul((double)cs, m_cell)), 1e-9);
+                hi = dsub(dadd(dadd(m_org, dmul((double)cs, m_cell)), m_cell), 1e-9);
             }
             const int cx = __shfl_sync(kFull, cs, lead), cy = __shfl_sync(kFull, cs, lead + 1), cz = __shfl_sync(kFull, cs, lead + 2);
             const int lim = (1 << 20) - 10;
             const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
-            dense_load_plane(a, cx, cy, cz, g, valid0 && in_range && !prev_done, pc);
-        }
-        B2_DTS(7);
-        {   // wait for the speculative loads here, in the shadow of the solve, not behind the barrier
-            int any = 0;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) any |= __float_as_int(pc.t[k].w);
-            asm volatile("" ::"r"(any));
+            spec_live = valid0 && in_range && !prev_done;
+            dense_load_plane(a, cx, cy, cz, g, spec_live, pc);
+            B2_DTS(7);
+            const float paf = (float)Pa_old;
+            const float Pxf = __shfl_sync(kFull, paf, lead), Pyf = __shfl_sync(kFull, paf, lead + 1), Pzf = __shfl_sync(kFull, paf, lead + 2);
+            // (consumes the loads: the wait sits here, in the shadow of the solve, not behind the barrier)
+            dense_screen_top2(a, pc, Pxf, Pyf, Pzf, m_cell, kp);
         }
         B2_DTS_MAX(12);
         named_sync(2, kDenseThreads);  // T_j is in sDS
@@ -497,41 +571,96 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         if (sDS.st.done) return;
         const double* sT = sDS.st.T;
         const double* sPivot = sDS.st.pivot;
-        double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        const float r_up = (float)prm.max_corr * 1.000001f;
         float4 pq = p_first;
+        double* colp = &sAccL[0][0] + col;
         const bool warp_has_queries = (int)(threadIdx.x >> 5) * kDenseQueriesPerWarp < share;
         for (int q0 = warp_has_queries ? warp_q0 : ns; q0 < ns; q0 += groups_total) {  // (warp-uniform trip count)
             const int q = q0 + grp;
             const bool valid = q < ns && has_query;
-            if (q0 != warp_q0 && valid) pq = __ldg(src + q);
+            const bool first = q0 == warp_q0;
+            if (!first && valid) pq = __ldg(src + q);
             double Pa = 0.0;
-            int ca = 0;
             if (g < 3) {
-                if (q0 == warp_q0) dense_axis_checked(sT + 4 * g, pdx, pdy, pdz, meta.origin[g], meta.cell, lo, hi, cs, Pa, ca);
-                else dense_axis(sT + 4 * g, pq, meta.origin[g], meta.cell, Pa, ca);
+                const double* row = sT + 4 * g;
+                Pa = dadd(dadd(dadd(dmul(row[0], (double)pq.x), dmul(row[1], (double)pq.y)), dmul(row[2], (double)pq.z)), row[3]);
             }
             const double Px = __shfl_sync(kFull, Pa, lead), Py = __shfl_sync(kFull, Pa, lead + 1), Pz = __shfl_sync(kFull, Pa, lead + 2);
-            const int cx = __shfl_sync(kFull, ca, lead), cy = __shfl_sync(kFull, ca, lead + 1), cz = __shfl_sync(kFull, ca, lead + 2);
-            const int lim = (1 << 20) - 10;
-            const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
-            // the speculative fetch stands when the cell did not change (first round); otherwise fetch now
+            double best = INFINITY;
+            int best_c = 0x7fffffff;
+            unsigned best_pos = 0;
+            float bx = 0.f, by = 0.f, bz = 0.f;
+            unsigned redo = kFull;  // lanes whose group has to take the full path (fetch around the new cell)
+            if (first) {
+                // ---- does the speculative screening stand under T_j?  The query moved by delta = |T_j p - T_{j-1} p|,
+                // so a cell at float32-screened distance D~ is now at least LB(D~) = D~ (1 - 4e-6) - 2 e_abs - delta
+                // away.  With rho = the exact distance of the nearest KEPT cell (capped at the gate r), the kept cells
+                // decide the search when (i) LB(third) > rho: no cell that was dropped can win, tie or match, and
+                // (ii) the ball of radius rho around the query lies inside the fetched 3 x 3 x 3 box (always true while
+                // the query stays in its cell: cell edge >= r).  The second-nearest is evaluated exactly only if
+                // LB(second) <= rho.  Anything else takes the full path.
+                const float fd = (float)dsub(Pa, Pa_old);
+                const float ddx = __shfl_sync(kFull, fd, lead), ddy = __shfl_sync(kFull, fd, lead + 1), ddz = __shfl_sync(kFull, fd, lead + 2);
+                const float delta = sqrt_approx(ddx * ddx + ddy * ddy + ddz * ddz) * 1.00001f + 1e-12f;
+                const int c1 = kp.c12 & 0xff, c2 = kp.c12 >> 8;
+                if (c1 != 0xff) {
+                    best = dist2_strict(Px, Py, Pz, (double)kp.x1, (double)kp.y1, (double)kp.z1);
+                    best_c = c1 + g;
+                    best_pos = kp.pos1;
+                    bx = kp.x1; by = kp.y1; bz = kp.z1;
+                }
+                const double gm = fmin(fmin(__shfl_sync(kFull, best, lead), __shfl_sync(kFull, best, lead + 1)), __shfl_sync(kFull, best, lead + 2));
+                const float rho = fminf(sqrt_approx((float)gm) * 1.000001f + 1e-30f, r_up);
+                bool ok = kp.s3 - delta > rho;
+                if (g < 3 && !(Pa > lo && Pa < hi)) {  // left the cell along this axis: distance to the face of the fetched box
+                    const double m = fmin(dsub(Pa, dsub(lo, m_cell)), dsub(dadd(hi, m_cell), Pa));
+                    ok = ok && ((float)m * 0.999999f - 4.0f * kp.e_abs > rho);
+                }
+                redo = __ballot_sync(kFull, valid && g < 3 && (!spec_live || !ok));
+                // a lane that cannot hold the minimum is no contender (the tail then takes its one-ballot path)
+                if (best > gm) best = INFINITY;
+                if (c2 != 0xff && kp.s2 - delta <= rho) {  // the second-nearest may be nearer (or tie) under T_j
+                    const double m2 = dist2_strict(Px, Py, Pz, (double)kp.x2, (double)kp.y2, (double)kp.z2);
+                    if (m2 < best || (m2 == best && c2 + g < best_c)) {
+                        best = m2; best_c = c2 + g; best_pos = kp.pos2;
+                        bx = kp.x2; by = kp.y2; bz = kp.z2;
+                    }
+                }
+            }
             B2_DTS(9);
+            if (redo) {  // (warp-uniform) the full path for the groups that need it
+                const bool gredo = ((redo >> lead) & 7u) != 0 && g < 3;
+                int ca = 0;
+                if (g < 3) ca = voxel_coord(Pa, m_org, m_cell);
+                const int cx = __shfl_sync(kFull, ca, lead), cy = __shfl_sync(kFull, ca, lead + 1), cz = __shfl_sync(kFull, ca, lead + 2);
+                const int lim = (1 << 20) - 10;
+                const bool in_range = cx > -lim && cx < lim && cy > -lim && cy < lim && cz > -lim && cz < lim;
 #ifdef B2_TAIL_TIMING
-            if (g == 0 && valid && j >= 0 && j < 64 && (cx != pc.cx || cy != pc.cy || cz != pc.cz)) atomicAdd(&g_dense_mis[j], 1u);
+                if (g == 0 && valid && gredo && first && j >= 0 && j < 64) atomicAdd(&g_dense_mis[j], 1u);
 #endif
-            if (q0 != warp_q0 || cx != pc.cx || cy != pc.cy || cz != pc.cz)
-                dense_load_plane(a, cx, cy, cz, g, valid && in_range, pc);
+                PlaneCells pc;
+                dense_load_plane(a, cx, cy, cz, g, gredo && valid && in_range, pc);
+                double sb;
+                int sc;
+                unsigned sp;
+                float sx, sy, sz;
+                dense_lane_best(m_cell, Px, Py, Pz, pc, g, lead, sb, sc, sp, sx, sy, sz);
+                if (gredo) {
+                    best = sb; best_c = sc; best_pos = sp;
+                    bx = sx; by = sy; bz = sz;
+                }
+            }
             B2_DTS(10);
             B2_DTS_MAX(13);
-            dense_finish(a, sPivot, meta.cell, Px, Py, Pz, pc, valid, q, g, lead, acc);
+            dense_group_tail(a, sPivot, Px, Py, Pz, best, best_c, best_pos, bx, by, bz, valid, q, g, lead, colp, first);
             B2_DTS(11);
         }
-        // the group's column: rows by lane role
-        if (g < kDenseLanes) {
-            sAccL[3 + g][col] = acc[0];
-            sAccL[6 + 3 * g][col] = acc[1]; sAccL[7 + 3 * g][col] = acc[2]; sAccL[8 + 3 * g][col] = acc[3];
-            sAccL[g][col] = acc[4];
-            if (g < 2) sAccL[15 + g][col] = acc[5];
+        // a warp without queries (or a source smaller than the grid) leaves zeros in its columns
+        if (g < kDenseLanes && !(warp_has_queries && warp_q0 < ns)) {
+            colp[(3 + g) * kDenseCols] = 0.0;
+            colp[(6 + 3 * g) * kDenseCols] = 0.0; colp[(7 + 3 * g) * kDenseCols] = 0.0; colp[(8 + 3 * g) * kDenseCols] = 0.0;
+            colp[g * kDenseCols] = 0.0;
+            if (g < 2) colp[(15 + g) * kDenseCols] = 0.0;
         }
     }
     __syncthreads();

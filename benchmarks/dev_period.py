@@ -14,8 +14,13 @@ scans, poses = bench.make_scans(scene, 12, dev, seed=1)
 prm = b2.make_params(0.05, 30)
 d4 = [eng.pack(s) for s in scans]
 eng.set_pose(poses[0])
+mis = np.zeros(64, dtype=np.uint32)
+eng.lib.b2_debug_dense_full_path.argtypes = [C.c_void_p]
 for s in d4:
     eng.slam_scan_dev(s, 0.02, prm)
+    eng.synchronize()
+    eng.lib.b2_debug_dense_full_path(mis.ctypes.data)
+    print("queries on the full path per launch:", mis[:34].tolist())
 eng.synchronize()
 res = eng.slam_results(1)[0]
 buf = np.zeros(64 * 148 * 16, dtype=np.uint64)
