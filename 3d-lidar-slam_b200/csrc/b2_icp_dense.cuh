@@ -545,6 +545,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         const bool valid0 = q_first < ns && has_query;
         double lo = 1.0, hi = 0.0;  // bounds of the predicted cell along this lane's axis (empty: nothing predicted)
         double Pa_old = 0.0;        // this lane's axis of T_{j-1} p
+        double pdx = (double)p_first.x, pdy = (double)p_first.y, pdz = (double)p_first.z;  // (converted in the shadow)
         bool spec_live;
         {
             PlaneCells pc;
@@ -572,18 +573,20 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         const double* sT = sDS.st.T;
         const double* sPivot = sDS.st.pivot;
         const float r_up = (float)prm.max_corr * 1.000001f;
-        float4 pq = p_first;
         double* colp = &sAccL[0][0] + col;
         const bool warp_has_queries = (int)(threadIdx.x >> 5) * kDenseQueriesPerWarp < share;
         for (int q0 = warp_has_queries ? warp_q0 : ns; q0 < ns; q0 += groups_total) {  // (warp-uniform trip count)
             const int q = q0 + grp;
             const bool valid = q < ns && has_query;
             const bool first = q0 == warp_q0;
-            if (!first && valid) pq = __ldg(src + q);
+            if (!first && valid) {
+                const float4 pq = __ldg(src + q);
+                pdx = (double)pq.x; pdy = (double)pq.y; pdz = (double)pq.z;
+            }
             double Pa = 0.0;
             if (g < 3) {
                 const double* row = sT + 4 * g;
-                Pa = dadd(dadd(dadd(dmul(row[0], (double)pq.x), dmul(row[1], (double)pq.y)), dmul(row[2], (double)pq.z)), row[3]);
+                Pa = dadd(dadd(dadd(dmul(row[0], pdx), dmul(row[1], pdy)), dmul(row[2], pdz)), row[3]);
             }
             const double Px = __shfl_sync(kFull, Pa, lead), Py = __shfl_sync(kFull, Pa, lead + 1), Pz = __shfl_sync(kFull, Pa, lead + 2);
             double best = INFINITY;
@@ -601,7 +604,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
                 // LB(second) <= rho.  Anything else takes the full path.
                 const float fd = (float)dsub(Pa, Pa_old);
                 const float ddx = __shfl_sync(kFull, fd, lead), ddy = __shfl_sync(kFull, fd, lead + 1), ddz = __shfl_sync(kFull, fd, lead + 2);
-                const float delta = sqrt_approx(ddx * ddx + ddy * ddy + ddz * ddz) * 1.00001f + 1e-12f;
+                const float delta = (fabsf(ddx) + fabsf(ddy) + fabsf(ddz)) * 1.00001f + 1e-12f;  // (>= the Euclidean norm)
                 const int c1 = kp.c12 & 0xff, c2 = kp.c12 >> 8;
                 if (c1 != 0xff) {
                     best = dist2_strict(Px, Py, Pz, (double)kp.x1, (double)kp.y1, (double)kp.z1);
