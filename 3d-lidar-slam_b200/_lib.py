@@ -22,7 +22,7 @@ EXPORTS = [
     "b2_version", "b2_create", "b2_destroy", "b2_last_error", "b2_set_stream", "b2_synchronize",
     "b2_launch_count", "b2_pack_xyz", "b2_unpack_xyz", "b2_project_pixels", "b2_voxel_downsample",
     "b2_estimate_normals", "b2_nn_search", "b2_icp", "b2_transform", "b2_map_init", "b2_map_reset",
-    "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_slam_scan", "b2_slam_set_pose",
+    "b2_map_fuse", "b2_map_size", "b2_map_export", "b2_map_icp", "b2_map_icp_corr", "b2_slam_scan", "b2_slam_set_pose",
     "b2_slam_get_pose", "b2_icp_batch", "b2_slam_scan_dev", "b2_map_stencil_candidates",
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
     "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results", "b2_icp_batch_p2l",
@@ -92,6 +92,7 @@ def load():
         "b2_map_export_records": [vp, vp, vp, i64, C.POINTER(i64)],
         "b2_map_merge_records": [vp, vp, vp, i64],
         "b2_map_icp": [vp, vp, i32, pd, C.POINTER(IcpParams), C.POINTER(IcpResult)],
+        "b2_map_icp_corr": [vp, vp, i32, pd, C.POINTER(IcpParams), C.POINTER(IcpResult), vp, vp],
         "b2_slam_scan": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan_dev": [vp, vp, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
         "b2_slam_scan_records": [vp, vp, i32, f64, f64, f64, f64, i32, f64, C.POINTER(IcpParams), C.POINTER(IcpResult)],
@@ -414,6 +415,19 @@ class Engine:
         res = IcpResult()
         self._check(self.lib.b2_map_icp(self.h, src.data_ptr(), src.shape[0], ip, C.byref(params), C.byref(res)))
         return res
+
+    def map_icp_corr(self, src, params: IcpParams, init=None):
+        """-> (result, d2 float64 [ns], match float32 [ns,4]): the registration plus the correspondence set of the
+        last evaluated transform (squared distances and matched voxel centroids, w = 1 where matched)."""
+        torch = self.torch
+        src = self._pts(src)
+        _i, ip = _dptr(init)
+        d2 = self.empty(src.shape[0], torch.float64)
+        match = self.empty((src.shape[0], 4), torch.float32)
+        res = IcpResult()
+        self._check(self.lib.b2_map_icp_corr(self.h, src.data_ptr(), src.shape[0], ip, C.byref(params), C.byref(res),
+                                             d2.data_ptr(), match.data_ptr()))
+        return res, d2, match
 
     def slam_scan(self, xyz_host: np.ndarray, ds_voxel: float, params: IcpParams, want_result: bool = True):
         """xyz_host: float32 [n,3] C-contiguous host array, pinned (uploaded in place) or pageable (staged

@@ -761,6 +761,50 @@ int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, co
     return B2_OK;
 }
 
+// matched centroid of every query from the brick-pool positions the dense step kernel reports
+__global__ void gather_matches_kernel(const int* __restrict__ pos, int n, const float4* __restrict__ cells,
+                                      float4* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int p = pos[q];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p >= 0) {
+        v = __ldg(cells + p);
+        v.w = 1.0f;
+    }
+    out[q] = v;
+}
+
+int b2_map_icp_corr(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
+                    b2_icp_result* out, double* d2_out_dev, float* match_out_dev) {
+    CTX(h);
+    B2_TRY(check_params(c, params));
+    if (ns <= 0 || !src_dev || !out || !d2_out_dev || !match_out_dev)
+        return set_error(c, B2_ERR_INVALID, "b2_map_icp_corr: empty cloud or NULL argument");
+    if (params->mode != B2_ICP_POINT_TO_POINT) return set_error(c, B2_ERR_INVALID, "the resident map holds no normals: point-to-point only");
+    B2_TRY(check_T(c, init, "b2_map_icp_corr"));
+    GridView g;
+    B2_TRY(map_grid_view(c, &g));
+    if (g.is_map != 2)
+        return set_error(c, B2_ERR_INVALID, "b2_map_icp_corr: per-query matches are reported for the brick-major map (voxel edge >= gate)");
+    if (params->max_correspondence_distance > map_max_corr(c) * (1.0 + 1e-12))
+        return set_error(c, B2_ERR_INVALID, "max_correspondence_distance %g exceeds the map's cell edge %g",
+                         params->max_correspondence_distance, map_max_corr(c));
+    double* init_dev = nullptr;
+    if (init) B2_TRY(upload_T(c, init, 5, &init_dev));
+    B2_WS(c, corr, int, WS_CORR, sizeof(int) * (size_t)ns);
+    IcpResultDev* res = map_result_dev(c);
+    B2_TRY(icp_run(c, (const float4*)src_dev, ns, nullptr, nullptr, 1, g, nullptr, nullptr, init_dev,
+                   to_internal(params), res, corr, d2_out_dev, 0, 0));
+    gather_matches_kernel<<<div_up(ns, 256), 256, 0, c->stream>>>(corr, ns, (const float4*)g.pts, (float4*)match_out_dev);
+    B2_LAUNCH_CHECK(c);
+    IcpResultDev* hr = (IcpResultDev*)((char*)c->host_mailbox + 1024);
+    B2_CUDA_OK(c, cudaMemcpyAsync(hr, res, sizeof(IcpResultDev), cudaMemcpyDeviceToHost, c->stream));
+    B2_TRY(check_status(c));
+    fill_result(hr, out);
+    return B2_OK;
+}
+
 int b2_stencil_candidates(b2_handle h, const float* src_dev, int ns, const float* tgt_dev, int nt, const double* T,
                           double cell, long long* n_candidates) {
     CTX(h);

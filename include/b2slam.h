@@ -185,6 +185,14 @@ int b2_map_merge_records(b2_handle h, const int* keys_dev, const double* sums_de
 int b2_map_icp(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
                b2_icp_result* out);
 
+/* The same registration, also reporting the correspondence set of the LAST evaluated transform — what Open3D's
+ * RegistrationResult.correspondence_set holds (icp_processor.py:103-113): d2_out_dev float64 [ns]
+ * squared distance of every source point to its nearest map voxel within the gate (0 where there is none),
+ * match_out_dev float32 [ns,4] that voxel's centroid (w = 1) or zeros.  When the iteration budget ends the
+ * registration, that transform is the result's.  Brick-major maps (voxel edge >= gate) only. */
+int b2_map_icp_corr(b2_handle h, const float* src_dev, int ns, const double* init, const b2_icp_params* params,
+                    b2_icp_result* out, double* d2_out_dev, float* match_out_dev);
+
 /* ---- fused per-scan step (ICPProcessor.construct_global_map, icp_processor.py:43-75) ---- */
 /* xyz_host: float32 [n,3] scan in the sensor frame (the plugin-boundary format).
  * Runs: upload -> voxel_down_sample(ds_voxel) -> ICP against the resident map seeded with

@@ -271,6 +271,64 @@ def test_map_icp_matches_oracle(engine, b2, pair0, driver):
         engine.map_icp(sd, b2.make_params(0.5, 30))
 
 
+def _check_dense_correspondences(engine, b2, sd, budget, init=None, rel=1e-6, gate=0.05):
+    """The correspondence set of the last evaluated transform (the result's) of the dense-map step kernel versus the
+    oracle's search with that very transform on the exported centroids: matched / unmatched, d2 and the matched
+    voxel (ties -> lowest canonical index) bit for bit."""
+    cent, _ = engine.map_export()
+    res, d2, match = engine.map_icp_corr(sd, b2.make_params(gate, budget, rel_fitness=rel, rel_rmse=rel), init=init)
+    tgt = f64(xyz(cent))
+    oidx, od2 = orc.nn_search(orc.transform(f64(xyz(sd)), res.matrix()), tgt, gate)
+    m = match.cpu().numpy()
+    np.testing.assert_array_equal(m[:, 3] > 0, oidx >= 0)
+    np.testing.assert_array_equal(d2.cpu().numpy(), od2)
+    hit = oidx >= 0
+    np.testing.assert_array_equal(m[hit, :3], xyz(cent)[oidx[hit]])
+    assert res.n_correspondences == int(hit.sum())
+    return res, hit
+
+
+@pytest.mark.parametrize("budget", [0, 1, 2, 3, 6, 12, 30])
+def test_dense_map_correspondences_of_the_result_transform_are_bit_exact(engine, b2, pair0, budget):
+    """Every launch of the dense-map ICP step after the first searches from what a speculative pass with the
+    PREVIOUS transform kept (b2_icp_dense.cuh); stopping the registration after `budget` steps exposes the search of
+    that step, large early updates and small late ones alike."""
+    src, tgt, _ = pair0
+    engine.map_init(0.05, [-9.0, -9.0, -9.0], 0.05, 1 << 18)
+    engine.map_fuse(engine.pack(tgt))
+    sd = _down(engine, src)
+    res, hit = _check_dense_correspondences(engine, b2, sd, budget, rel=0.0 if budget < 30 else 1e-6)
+    assert res.iterations == budget or budget == 30
+    assert 0.3 < hit.mean() < 1.0  # matched and unmatched queries both occur
+    # a start far from the answer: the first updates move queries across several cells
+    T0 = np.eye(4)
+    T0[:3, 3] = [0.06, -0.05, 0.04]
+    _check_dense_correspondences(engine, b2, sd, budget, init=T0, rel=0.0)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_dense_map_correspondences_on_lattice_clouds(engine, b2, seed):
+    """Voxel centroids on a 1/16 m lattice and queries on the half-lattice (every coordinate exactly representable):
+    distances tie exactly between two, four and eight voxels, queries sit exactly on voxel faces and neighbours lie
+    at exactly the gate (rejected: d2 < r2 is strict) — under the identity, a lattice-preserving start and a generic
+    one."""
+    rng = np.random.default_rng(seed)
+    v = 0.0625
+    tgt = ((rng.integers(-30, 30, (20000, 3)) + 0.5) * v).astype(np.float32)  # voxel centres, many voxels hit twice
+    src = (rng.integers(-60, 60, (6000, 3)) * (v / 2)).astype(np.float32)
+    engine.map_init(v, [-4.0, -4.0, -4.0], v, 1 << 18)
+    engine.map_fuse(engine.pack(tgt))
+    sd = engine.pack(src)
+    for budget in (0, 1, 4):
+        _, hit = _check_dense_correspondences(engine, b2, sd, budget, rel=0.0, gate=v)
+        assert hit.any() and (~hit).any()
+    T0 = np.eye(4)
+    T0[:3, 3] = [v / 4, 0.0, -v / 2]
+    _check_dense_correspondences(engine, b2, sd, 2, init=T0, rel=0.0, gate=v)
+    T0[:3, 3] = [0.0131, -0.0072, 0.0205]
+    _check_dense_correspondences(engine, b2, sd, 3, init=T0, rel=0.0, gate=v)
+
+
 def test_map_capacity_error(engine, b2, pair0):
     src, _, _ = pair0
     engine.map_init(0.02, [-9.0, -9.0, -9.0], 0.02, 1024)
