@@ -65,7 +65,7 @@ SCENE_SEED = 1000
 START_X = 20.0
 METRIC = "scans/s ICP+fuse (49k-pt scan->2M-pt map)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, `ncu --set full`
-# (profiles/r02/icp_dense_2M_full_raw.csv; cold caches between replays)
+# (profiles/r02/icp_dense_2M_spec_full_raw.csv; cold caches between replays)
 ICP_DENSE_TRAFFIC = int(os.environ.get("B2_BENCH_TRAFFIC", 0)) or None
 
 
@@ -461,7 +461,7 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
     us_eager = ev0.elapsed_time(ev1) * 1e3 / (reps * n_launch)
     # the same kernel where the timed region runs it: inside the graph-replayed scan step.  Two budgets with the
     # convergence test disabled (every launch active); the difference of the step times is (30 - 6) ICP launches.
-    def scan_step_us(iters, n=24):
+    def scan_step_us(iters, n=min(24, len(dev_scans))):
         prm_i = b2.make_params(MAX_CORR, iters, rel_fitness=0.0, rel_rmse=0.0)
         for rep in range(2):   # first pass: eager + capture per parity, second pass: timed replays
             eng.set_pose(poses[0])
@@ -514,7 +514,7 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
 
 
 # traffic of the dense kernel from the committed ncu capture (bytes per launch); see profiles/README.md
-ICP_DENSE_TRAFFIC_DEFAULT = 773_600
+ICP_DENSE_TRAFFIC_DEFAULT = 773_100
 
 
 def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2batch):
