@@ -306,6 +306,19 @@ def test_dense_map_correspondences_of_the_result_transform_are_bit_exact(engine,
     _check_dense_correspondences(engine, b2, sd, budget, init=T0, rel=0.0)
 
 
+def test_dense_map_correspondences_with_more_queries_than_one_round(engine, b2, pair0):
+    """A raw 49,152-pt source is more than the 148 x 190 queries the step kernel serves per round: the first round
+    searches from the speculative pass, the second one takes the full path — both must agree with the oracle.  Also
+    tiny sources (fewer queries than CTAs, than lanes of a warp)."""
+    src, tgt, _ = pair0
+    engine.map_init(0.05, [-9.0, -9.0, -9.0], 0.05, 1 << 18)
+    engine.map_fuse(engine.pack(tgt))
+    for budget in (1, 4):
+        _check_dense_correspondences(engine, b2, engine.pack(src), budget, rel=0.0)
+    for n in (1, 2, 11, 149, 1481):
+        _check_dense_correspondences(engine, b2, engine.pack(src[:: len(src) // n][:n].copy()), 3, rel=0.0)
+
+
 @pytest.mark.parametrize("seed", [0, 1])
 def test_dense_map_correspondences_on_lattice_clouds(engine, b2, seed):
     """Voxel centroids on a 1/16 m lattice and queries on the half-lattice (every coordinate exactly representable):
