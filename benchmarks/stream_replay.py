@@ -126,6 +126,10 @@ def main():
         "scans_per_s_e2e": round(n / times.sum(), 1), "seconds": round(float(times.sum()), 3),
         "first_100_scans_per_s": round(h / times[5:5 + h].sum(), 1) if n > h + 5 else None,
         "last_100_scans_per_s": round(h / times[-h:].sum(), 1),
+        "frame_us": {"median": round(float(np.median(times)) * 1e6, 1), "p99": round(float(np.percentile(times, 99)) * 1e6, 1),
+                     "max": round(float(times.max()) * 1e6, 1), "argmax": int(times.argmax()),
+                     "note": "wall time of one construct_global_map + pose read; a max far above the median is a host "
+                             "stall of that frame (the replay shares the box's cores with the scan synthesis threads)"},
         "scan_synthesis_s": round(t_gen, 1),
         "map_voxels_over_time": sizes, "final_map_voxels": sizes[-1],
         "drift_m": {"max": round(max(errs), 4), "final": round(errs[-1], 4)},
