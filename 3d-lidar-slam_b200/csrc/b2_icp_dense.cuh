@@ -12,15 +12,18 @@
 //     a launch never overwrites what a slower CTA of the same launch still has to read; CTA 0 alone publishes the
 //     state / result records.  A registration of I steps is I + 2 launches: launch 0 only searches, launch I + 1
 //     only folds and finishes.
-//   * the fold + solve (one thread's worth of dependent fp64, ~2.5 us) runs on a 21st CONTROL WARP while the 20
-//     search warps run the memory half of the search SPECULATIVELY with the previous transform T_{j-1}: an ICP
-//     update moves a query by far less than a 5 cm cell after the first steps, so the cell it lands in — hence
-//     the bricks and the 27 stencil cells to fetch — is almost always the one T_j will give.  The candidates
-//     wait in registers; when T_j arrives (named barrier), a query whose cell did change reloads, the others go
-//     straight to the distances.  Hash probes and cell loads are off the critical path.
-//   * distances are screened in float32 (full-rate pipes, no fp32->fp64 conversions) and only the contenders —
-//     candidates within the float32 error bound of the best — are evaluated in un-fused fp64 in the oracle's
-//     order, so correspondences, d2 and ties are bit-identical to the all-fp64 search.
+//   * the fold + solve (one thread's worth of dependent fp64, ~2 us) runs on a 20th CONTROL WARP while the 19
+//     search warps run the search SPECULATIVELY with the previous transform T_{j-1}: an ICP update moves a query
+//     by far less than a 5 cm cell after the first steps, so the cell it lands in, the bricks, the 27 stencil cells
+//     AND the ranking of those cells by distance are almost always what T_j will give.  Each lane fetches its nine
+//     cells, screens them in float32 and keeps its two nearest cells plus a lower bound for the rest (SpecKept).
+//     When T_j arrives (named barrier) the query has moved by a measured delta; if the bound minus delta still
+//     exceeds the exact distance of the nearest kept cell (and the query has not left the fetched box), the kept
+//     cells decide the search: one exact d2 per lane.  Anything else takes the full path around the new cell.
+//     Probes, cell loads and the screening are off the critical path.
+//   * distances are screened in float32 (full-rate pipes, no fp32->fp64 conversions) and only the contenders are
+//     evaluated in un-fused fp64 in the oracle's order, so correspondences, d2 and ties are bit-identical to an
+//     all-fp64 search (tests/test_gpu_parity.py::test_dense_map_correspondences_*).
 #ifdef B2_TAIL_TIMING
 __device__ unsigned long long g_dense_ts[64 * 148 * 16];
 __device__ unsigned g_dense_mis[64];
