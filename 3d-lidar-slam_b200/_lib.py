@@ -27,6 +27,7 @@ EXPORTS = [
     "b2_radius_outlier_mask", "b2_statistical_outlier_mask", "b2_select_points", "b2_stencil_candidates",
     "b2_set_icp_driver", "b2_ingest_pointcloud2", "b2_slam_results", "b2_icp_batch_p2l",
     "b2_estimate_normals_batch", "b2_map_export_records", "b2_map_merge_records", "b2_set_scan_path", "b2_scan_downsample", "b2_slam_scan_records",
+    "b2_set_dense_driver",
 ]
 
 
@@ -67,6 +68,7 @@ def load():
     lib.b2_last_error.argtypes = [vp]
     lib.b2_set_icp_driver.argtypes = [vp, i32]
     lib.b2_set_scan_path.argtypes = [vp, i32]
+    lib.b2_set_dense_driver.argtypes = [vp, i32]
     lib.b2_launch_count.restype = C.c_ulonglong
     lib.b2_launch_count.argtypes = [vp]
     protos = {
@@ -204,6 +206,12 @@ class Engine:
         """'hash' (default: sort-free scratch-hash passes) | 'sorted' (radix-sort pipeline) for slam_scan*."""
         code = {"hash": 0, "sorted": 1}.get(path, path)
         self._check(self.lib.b2_set_scan_path(self.h, int(code)))
+
+    def set_dense_driver(self, driver) -> None:
+        """'persistent' (default: one launch per registration against the brick-major map) | 'chained' (one launch
+        per ICP step)."""
+        code = {"persistent": 0, "chained": 1}.get(driver, driver)
+        self._check(self.lib.b2_set_dense_driver(self.h, int(code)))
 
     def launch_count(self) -> int:
         return int(self.lib.b2_launch_count(self.h))

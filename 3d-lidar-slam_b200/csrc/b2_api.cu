@@ -254,6 +254,8 @@ int b2_create(int device, b2_handle* out) {
     if (cudaSetDevice(device) != cudaSuccess) return B2_ERR_CUDA;
     Context* c = new Context();
     c->scan_path = getenv("B2_STREAM_SORTED") ? B2_SCAN_PATH_SORTED : B2_SCAN_PATH_HASH;
+    c->dense_driver = (getenv("B2_DENSE_PERSIST") && atoi(getenv("B2_DENSE_PERSIST")) == 0) ? B2_DENSE_DRIVER_CHAINED
+                                                                                              : B2_DENSE_DRIVER_PERSISTENT;
     c->device = device;
     // the main stream (ICP chain, fusion) outranks the front stream (uploads, down-sample of the NEXT scan), whose
     // CTAs only fill what the ICP chain leaves free
@@ -375,6 +377,17 @@ int b2_set_scan_path(b2_handle h, int path) {
     if (c->scan_path != path) {
         c->scan_path = path;
         c->ws_generation++;  // the captured scan step holds the other path's kernels
+    }
+    return B2_OK;
+}
+
+int b2_set_dense_driver(b2_handle h, int driver) {
+    CTX(h);
+    if (driver != B2_DENSE_DRIVER_PERSISTENT && driver != B2_DENSE_DRIVER_CHAINED)
+        return set_error(c, B2_ERR_INVALID, "b2_set_dense_driver: unknown driver %d", driver);
+    if (c->dense_driver != driver) {
+        c->dense_driver = driver;
+        c->ws_generation++;  // the captured scan step holds the other driver's launches
     }
     return B2_OK;
 }

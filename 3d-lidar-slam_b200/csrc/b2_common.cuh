@@ -62,6 +62,7 @@ struct ScanGraph {
 struct Context {
     int icp_driver = 0;  // B2_ICP_DRIVER_*
     int scan_path = 0;   // B2_SCAN_PATH_*
+    int dense_driver = 0;  // B2_DENSE_DRIVER_*
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;

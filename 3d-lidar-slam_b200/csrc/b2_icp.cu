@@ -96,6 +96,7 @@ void launch_iter(Context* c, dim3 grid, const float4* src, const int* src_offs, 
                        search_only, loop_handle, spread_partial);
 }
 
+template <bool PERSIST>
 void launch_dense(Context* c, dim3 grid, const float4* src, const int* ns_dev, int ns_max, const GridView& g,
                   const IcpParams& prm, DenseState* states, long long* seqw, double* partial, IcpResultDev* res, int* corr,
                   int* ndone, double* d2_out, int step, cudaStream_t stream, unsigned long long loop_handle) {
@@ -109,9 +110,9 @@ void launch_dense(Context* c, dim3 grid, const float4* src, const int* ns_dev, i
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     static const bool no_pdl = getenv("B2_NO_PDL") != nullptr;
     cfg.attrs = attr;
-    cfg.numAttrs = no_pdl ? 0 : 1;
-    cudaLaunchKernelEx(&cfg, icp_dense_kernel, src, ns_dev, ns_max, (const BrickEntry*)g.btab, g.mask,
-                       (const float4*)g.pts, (const GridMeta*)g.meta, prm, states, seqw, partial, res, corr, ndone, d2_out, step, loop_handle);
+    cfg.numAttrs = (no_pdl || PERSIST) ? 0 : 1;  // (the persistent variant starts after the init kernel has completed)
+    cudaLaunchKernelEx(&cfg, icp_dense_kernel<PERSIST>, src, ns_dev, ns_max, (const BrickEntry*)g.btab, g.mask,
+                       (const float4*)g.pts, (const GridMeta*)g.meta, prm, states, seqw, partial, res, corr, ndone, d2_out, step, loop_handle, c->dev_status);
 }
 
 template <int MODE, int KIND, int L>
@@ -299,9 +300,10 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     if (dense && (prm.mode != 0 || n_pairs != 1 || src_offsets || search_only))
         return set_error(c, B2_ERR_INVALID, "the dense resident map registers one point-to-point scan at a time");
     B2_WS(c, states, IcpState, WS_ICP_STATE, sizeof(IcpState) * (size_t)n_pairs);
-    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs * 2);
+    // (+ 8 KB: the persistent dense variant keeps 2 x 148 x 17 tagged 16-byte entries here)
+    B2_WS(c, partial, double, WS_ICP_PARTIAL, sizeof(double) * kTerms * (size_t)(gx > kCtasPerSm * kSMs ? gx : kCtasPerSm * kSMs) * n_pairs * 2 + 8192);
     B2_WS(c, tickets, int, WS_ICP_TICKET, sizeof(int) * ((size_t)n_pairs + 1));
-    B2_WS(c, dstates, DenseState, WS_ICP_DENSE, sizeof(DenseState) * 2 + sizeof(long long));
+    B2_WS(c, dstates, DenseState, WS_ICP_DENSE, sizeof(DenseState) * 2 + 2 * sizeof(long long));  // + seqw, grid-barrier word
     long long* seqw = reinterpret_cast<long long*>(dstates + 2);
     int* ndone = tickets + n_pairs;
     if (dense)
@@ -311,7 +313,9 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
                                                                      states, tickets, ndone, n_pairs);
     B2_LAUNCH_CHECK(c);
     dim3 g(gx, n_pairs);
-    const int launches = search_only ? 1 : prm.max_iter + 1 + (dense ? 1 : 0);
+    // the dense-map registration as ONE persistent launch (b2_set_dense_driver; every CTA of the grid must be resident)
+    const bool dense_persist = dense && c->dense_driver == B2_DENSE_DRIVER_PERSISTENT && gx <= kCtasPerSm * kSMs;
+    const int launches = search_only ? 1 : (dense_persist ? 1 : prm.max_iter + 1 + (dense ? 1 : 0));
 #ifdef B2_EXPERIMENTS
     // (opt-in: on B200 the software grid barrier + solve of a step costs more than a kernel boundary)
     static const bool persist = getenv("B2_PERSIST") != nullptr;
@@ -361,12 +365,17 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     // B2_ICP_WHILE=0 disables the loop node, =1 uses it for every step.
     static const char* while_env = getenv("B2_ICP_WHILE");
     const int while_mode = while_env ? atoi(while_env) : -1;
-    const bool can_while = c->capturing && n_pairs == 1 && !sweep && !search_only && !corr_out && !d2_out && while_mode != 0;
+    const bool can_while = c->capturing && n_pairs == 1 && !sweep && !search_only && !corr_out && !d2_out && while_mode != 0 && !dense_persist;
     const int chained = !can_while ? launches : (while_mode == 1 ? 0 : (launches > kChainSteps ? kChainSteps : launches));
     auto launch_one = [&](cudaStream_t launch_stream, unsigned long long loop_handle, int step) {
+        if (dense_persist) {
+            launch_dense<true>(c, g, src, ns_dev, ns_max, grid, prm, dstates, seqw, partial, results_dev, corr_out, ndone,
+                               d2_out, prm.max_iter + 2, launch_stream, 0ull);
+            return;
+        }
         if (dense) {
-            launch_dense(c, g, src, ns_dev, ns_max, grid, prm, dstates, seqw, partial, results_dev, corr_out, ndone,
-                         d2_out, step, launch_stream, loop_handle);
+            launch_dense<false>(c, g, src, ns_dev, ns_max, grid, prm, dstates, seqw, partial, results_dev, corr_out, ndone,
+                                d2_out, step, launch_stream, loop_handle);
             return;
         }
 #define B2_ICP_LAUNCH(M, K)                                                                                   \

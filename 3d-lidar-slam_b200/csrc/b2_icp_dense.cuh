@@ -54,6 +54,9 @@ struct DenseState {
 __global__ void icp_dense_init_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
                                       const double* __restrict__ init, DenseState* __restrict__ states,
                                       long long* __restrict__ seqw, int* __restrict__ ndone) {
+    // persistent variant: a fresh epoch per registration, so that a partial left by an earlier registration can never
+    // pass for one of this one (the partials carry (epoch, step) tags instead of being fenced by a barrier)
+    reinterpret_cast<unsigned*>(seqw + 1)[0] += 1u;
     // launch 0 reads slot 1 (parity of "launch -1")
     DenseState s;
     for (int i = 0; i < 16; ++i) s.st.T[i] = init ? init[i] : ((i % 5 == 0) ? 1.0 : 0.0);
@@ -422,15 +425,39 @@ __device__ __forceinline__ void dense_group_tail(const DenseArgs& a, const doubl
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// step >= 0: index of this launch in the chain (parity baked in by the host); step < 0: body of a CUDA-graph
-// WHILE node — the launch index is read from *seqw first (one more round trip, only in the tail of long budgets).
+// Tagged partials of the persistent variant: every fp64 term travels as a 16-byte entry {lo, tag, hi, tag}.  Each
+// 8-byte half validates itself, so an entry is complete as soon as both tags read (epoch, step) — no fence, no
+// arrival counter and no second round trip between "everybody has arrived" and "now load the data": the CTAs poll the
+// data itself, and the last partial to arrive IS the grid barrier.
+// (vector accesses are performed element by element and a naturally aligned 64-bit element is single-copy atomic: the
+// elements are the two {value half, tag} words)
+__device__ __forceinline__ void st_tagged(uint4* p, double v, unsigned tag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v), t = (unsigned long long)tag << 32;
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"((b & 0xffffffffull) | t), "l"((b >> 32) | t) : "memory");
+}
+__device__ __forceinline__ uint4 ld_tagged(const uint4* p) {  // -> {lo, tag, hi, tag}
+    unsigned long long w0, w1;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+    return make_uint4((unsigned)w0, (unsigned)(w0 >> 32), (unsigned)w1, (unsigned)(w1 >> 32));
+}
+
+// PERSIST == false — one launch per step.  step >= 0: index of this launch in the chain (parity baked in by the host);
+// step < 0: body of a CUDA-graph WHILE node — the launch index is read from *seqw first (one more round trip, only in
+// the tail of long budgets).
+// PERSIST == true — ONE launch per registration: the steps are trips of a loop, `step` is their maximum number, and
+// the kernel boundary between two steps is replaced by a grid barrier (arrival counter in global memory; one CTA per
+// SM, all co-resident) — and the barrier is implicit: the only thing CTAs exchange is their partial sums, which
+// travel as self-validating tagged entries (st_tagged / ld_tagged), so a CTA simply polls the 148 partials it needs.
+// The state record then never leaves shared memory, the query point, its doubles and the map metadata stay in
+// registers, and the launches that would only find "done" do not exist.
+template <bool PERSIST>
 __global__ void __launch_bounds__(kDenseThreads, 1)
 icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev, int ns_max,
                  const BrickEntry* __restrict__ btab, unsigned bmask, const float4* __restrict__ cells,
                  const GridMeta* __restrict__ metas, IcpParams prm,
                  DenseState* __restrict__ states, long long* __restrict__ seqw, double* __restrict__ partial,
                  IcpResultDev* __restrict__ results, int* __restrict__ corr_out, int* __restrict__ ndone,
-                 double* __restrict__ d2_out, int step, unsigned long long loop_handle) {
+                 double* __restrict__ d2_out, int step, unsigned long long loop_handle, int* __restrict__ status) {
     constexpr int NT = 17;
     constexpr int kParts = kDenseSearchThreads / 32;  // 20
     __shared__ DenseState sDS;
@@ -438,9 +465,9 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     __shared__ double sRed[kParts][kTerms];
     static_assert(sizeof(DenseState) % 8 == 0 && sizeof(GridMeta) % 8 == 0, "copied as 8-byte words");
 
-    long long j = step;
+    long long j = PERSIST ? 0 : step;
     B2_DTS(0);
-    asm volatile("griddepcontrol.launch_dependents;");
+    if (!PERSIST) asm volatile("griddepcontrol.launch_dependents;");
     const bool control = threadIdx.x >= kDenseSearchThreads;
     const int lane = threadIdx.x & 31;
     const int grp = min(lane / kDenseLanes, kDenseQueriesPerWarp - 1);  // (lanes 30, 31: g = 3, 4 -> idle)
@@ -463,20 +490,26 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
     const double m_org = __ldg(&metas->origin[lane < 30 ? lane % 3 : 0]);   // this lane's axis of the map origin
     float4 p_first = make_float4(0.f, 0.f, 0.f, 0.f);
     if (!control && has_query && q_first < ns) p_first = __ldg(src + q_first);  // (one address per group)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (!PERSIST) asm volatile("griddepcontrol.wait;" ::: "memory");
     B2_DTS(1);
-    if (step < 0) j = __ldcg(seqw);
-    const int rd = (int)((j + 1) & 1), wr = (int)(j & 1);
-    const DenseState* prev = states + rd;
+    if (!PERSIST && step < 0) j = __ldcg(seqw);
 
     DenseArgs a;
     a.btab = btab; a.bmask = bmask; a.cells = cells;
     a.r2 = dmul(prm.max_corr, prm.max_corr);
     a.corr_out = corr_out; a.d2_out = d2_out;
-
+    const unsigned epoch_tag = PERSIST ? __ldcg(reinterpret_cast<const unsigned*>(seqw + 1)) << 10 : 0u;  // (steps < 1024)
+    if (PERSIST) {  // the state record stays in shared memory for the whole registration
+        if (control && lane < (int)(sizeof(DenseState) / 8))
+            reinterpret_cast<double*>(&sDS)[lane] = __ldcg(reinterpret_cast<const double*>(states + 1) + lane);
+        __syncthreads();
+    }
+  for (;;) {  // (PERSIST: one trip per step; otherwise a single trip)
+    const int rd = (int)((j + 1) & 1), wr = (int)(j & 1);
+    const DenseState* prev = states + rd;
     if (control) {
         // ---- control warp: state record, fold of the previous launch's partials, the A.3 step -----------------
-        if (lane < (int)(sizeof(DenseState) / 8))
+        if (!PERSIST && lane < (int)(sizeof(DenseState) / 8))
             reinterpret_cast<double*>(&sDS)[lane] = __ldcg(reinterpret_cast<const double*>(prev) + lane);
         if (lane < kDenseCols - kDenseLeaders)  // (the fold reads columns in chunks of 32: zero the padding columns)
             for (int t = 0; t < NT; ++t) sAccL[t][kDenseLeaders + lane] = 0.0;
@@ -497,7 +530,7 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         }
         if (lane == 0) {
             sDS.seq = j + 1;
-            if (blockIdx.x == 0) {
+            if (!PERSIST && blockIdx.x == 0) {
                 states[wr] = sDS;
                 *seqw = j + 1;
                 if (loop_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)loop_handle, sDS.st.done ? 0u : 1u);
@@ -507,15 +540,45 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         B2_DTS(3);
         named_sync(2, kDenseThreads);  // T_j (or `done`) is in sDS
         if (sDS.st.done) return;
-        __syncthreads();               // (the search warps' columns are complete; the control warp has no part in the fold)
-        return;
-    }
-
+    } else {
     // ---- search warps ----------------------------------------------------------------------------------------------
     // (a) this thread's share of the previous launch's partials: part = warp, term = lane
-    {
         double s = 0.0;
-        if (j > 0 && lane < NT) {
+        if (PERSIST) {
+            if (j > 0 && lane < NT) {
+                constexpr int kMaxPer = (kCtasPerSm * kSMs + kParts - 1) / kParts;
+                const uint4* pp = reinterpret_cast<const uint4*>(partial) + (size_t)rd * kCtasPerSm * kSMs * NT + lane;
+                const int part = threadIdx.x >> 5;
+                const unsigned tag = epoch_tag + (unsigned)j;  // written at the end of trip j - 1
+                double v[kMaxPer];
+                unsigned pending = 0;
+#pragma unroll
+                for (int k = 0; k < kMaxPer; ++k) {
+                    v[k] = 0.0;
+                    if (part + k * kParts < n_cta) pending |= 1u << k;
+                }
+                // (every warp polls the entries it needs: a cheaper hint phase in front — one entry per row — and a
+                // back-off between the rounds were both measured slower: what counts is the number of round trips
+                // between the last partial landing and the fold, not the 6 MB per round the polling moves)
+                for (unsigned spins = 0; pending; ++spins) {
+#pragma unroll
+                    for (int k = 0; k < kMaxPer; ++k) {
+                        if (!(pending >> k & 1u)) continue;
+                        const uint4 e = ld_tagged(pp + (size_t)(part + k * kParts) * NT);
+                        if (e.y == tag && e.w == tag) {
+                            v[k] = __longlong_as_double((long long)(((unsigned long long)e.z << 32) | e.x));
+                            pending &= ~(1u << k);
+                        }
+                    }
+                    if (spins > (1u << 20)) {  // (seconds: some CTA of the grid is not resident — never with one CTA per SM)
+                        atomicCAS(status, 0, B2_ERR_STATE);
+                        break;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kMaxPer; ++k) s += v[k];
+            }
+        } else if (j > 0 && lane < NT) {
             constexpr int kMaxPer = (kCtasPerSm * kSMs + kParts - 1) / kParts;
             const double* pp = partial + (size_t)rd * kCtasPerSm * kSMs * kTerms + lane;
             const int part = threadIdx.x >> 5;
@@ -530,8 +593,10 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
         }
         // (b) meanwhile: the previous transform for the speculative fetch — ONE request per warp (the record is a
         // single line that 148 x 19 warps read at the same moment), rows handed out by shuffles
-        const double tv = lane < 12 ? __ldg(prev->st.T + lane) : 0.0;
-        const int prev_done = __ldg(&prev->st.done);
+        // (PERSIST: the state record of the previous trip is in shared memory; the control warp rewrites it only
+        // after this warp has arrived at barrier 1, and a finished registration never gets here)
+        const double tv = lane < 12 ? (PERSIST ? sDS.st.T[lane] : __ldg(prev->st.T + lane)) : 0.0;
+        const int prev_done = PERSIST ? 0 : __ldg(&prev->st.done);
         double Trow[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) Trow[i] = __shfl_sync(kFull, tv, (4 * g + i) & 15);
@@ -669,8 +734,28 @@ icp_dense_kernel(const float4* __restrict__ src, const int* __restrict__ ns_dev,
             if (g < 2) colp[(15 + g) * kDenseCols] = 0.0;
         }
     }
-    __syncthreads();
+    __syncthreads();  // (the search warps' columns are complete; the control warp has no part in the fold)
     B2_DTS(4);
-    cta_fold<NT, kDenseCols>(&sAccL[0][0], partial + ((size_t)wr * kCtasPerSm * kSMs + blockIdx.x) * kTerms);
+    if (!PERSIST) {
+        cta_fold<NT, kDenseCols>(&sAccL[0][0], partial + ((size_t)wr * kCtasPerSm * kSMs + blockIdx.x) * kTerms);
+        B2_DTS(5);
+        return;
+    }
+    {   // the same fold, the partial published as tagged entries (tag of trip j: read by everybody in trip j + 1)
+        uint4* out = reinterpret_cast<uint4*>(partial) + ((size_t)wr * kCtasPerSm * kSMs + blockIdx.x) * NT;
+        const int w = threadIdx.x >> 5;
+        for (int t = w; t < NT; t += kDenseThreads / 32) {
+            double acc = 0.0;
+#pragma unroll
+            for (int c0 = 0; c0 < kDenseCols; c0 += 32) acc += sAccL[t][c0 + lane];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+            if (lane == 0) st_tagged(out + t, acc, epoch_tag + (unsigned)(j + 1));
+        }
+    }
     B2_DTS(5);
+    __syncthreads();  // (the columns are rewritten by the next trip)
+    ++j;
+    if (j >= step) return;
+  }
 }

@@ -34,6 +34,18 @@ first = ts[:n, :, 0].min(axis=1)
 last_exit = ts[:n, :, 5].max(axis=1)
 print("launch-to-launch period (first entry), ns:", np.diff(first)[:n - 1].tolist())
 print("gap last exit -> next first entry, ns:", (first[1:n] - last_exit[:n - 1]).tolist())
+persist = bool(int(os.environ.get("B2_DENSE_PERSIST", "0")))
+if persist:  # one launch: no per-step entry stamps; refer every trip to its first "arrived" stamp, ignore stale slots
+    for jj in (5, 10):
+        ref = ts[jj, :, 6].min()
+        def stat(k):
+            v = ts[jj, :, k] - ref
+            v = v[(v >= 0) & (v < 100000)]
+            return f"{int(v.mean())}/{int(v.max())}" if len(v) else "-"
+        print(f"trip {jj} (ns after the first warp-0 arrival): " + "  ".join(f"{names[k]} {stat(k)}" for k in range(2, 15)))
+    arr = np.array([ts[jj, :, 6].min() for jj in range(2, n - 1)])
+    print("trip-to-trip period (first arrival), ns:", np.diff(arr).tolist())
+    sys.exit(0)
 for jj in (5, 10):
     t0 = first[jj]
     print(f"launch {jj}: " + "  ".join(f"{names[k]} {int((ts[jj, :, k] - t0).mean())}/{int((ts[jj, :, k] - t0).max())}" for k in range(15)))

@@ -85,6 +85,16 @@ int b2_set_icp_driver(b2_handle h, int driver);
 #define B2_SCAN_PATH_HASH 0
 #define B2_SCAN_PATH_SORTED 1
 int b2_set_scan_path(b2_handle h, int path);
+/* How a registration against the brick-major resident map (voxel edge >= gate) is launched; results are identical bit
+ * for bit (the same kernel body, tests run both):
+ * B2_DENSE_DRIVER_PERSISTENT (default) = ONE launch per registration: one CTA per SM stays resident, the ICP steps
+ *   are trips of a loop, and the CTAs exchange their partial sums as self-validating tagged records they poll for
+ *   (no kernel boundary, no launches that only find "done");
+ * B2_DENSE_DRIVER_CHAINED = one launch per ICP step, chained with programmatic dependent launch (+ a CUDA-graph
+ *   WHILE node beyond 40 steps).  The environment variable B2_DENSE_PERSIST=0 selects CHAINED at b2_create. */
+#define B2_DENSE_DRIVER_PERSISTENT 0
+#define B2_DENSE_DRIVER_CHAINED 1
+int b2_set_dense_driver(b2_handle h, int driver);
 
 /* ---- layout helpers ----------------------------------------------------- */
 /* float32 [n,3] (host when src_on_host != 0, else device) -> float32 [n,4] device rows.

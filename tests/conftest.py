@@ -57,6 +57,16 @@ def driver(request, engine):
     engine.set_icp_driver("auto")
 
 
+@pytest.fixture(params=["persistent", "chained"])
+def dense_driver(request, engine):
+    """Run a test under both launch schemes of a registration against the brick-major resident map
+    (include/b2slam.h B2_DENSE_DRIVER_*): one persistent launch, or one launch per ICP step.  Same kernel body,
+    identical results."""
+    engine.set_dense_driver(request.param)
+    yield request.param
+    engine.set_dense_driver("persistent")
+
+
 @pytest.fixture(scope="session")
 def pair0():
     """Config-1-shaped pair (seed 0): float32 source / target scans and the true relative pose."""

@@ -63,7 +63,7 @@ def test_full_size_scan_to_map_registration(engine, b2, big_map):
     assert before <= after < before + 3000  # a registered scan lands almost entirely in existing voxels
 
 
-def test_full_size_config2_registration_matches_the_oracle(engine, b2, big_map):
+def test_full_size_config2_registration_matches_the_oracle(engine, b2, big_map, dense_driver):
     """BASELINE config 2 at full size (icp_processor.py:103-113): three consecutive 49k-pt scans, each 2 cm
     down-sampled and registered against the 2 M-voxel map by the dense-map step kernel, versus
     ``registration_icp`` of the oracle on the map's exported centroids.  Iterations, correspondence count and

@@ -255,7 +255,7 @@ def test_map_fuse_export_matches_oracle(engine, pair0, voxel, max_corr):
     assert engine.map_size() == 0
 
 
-def test_map_icp_matches_oracle(engine, b2, pair0, driver):
+def test_map_icp_matches_oracle(engine, b2, pair0, driver, dense_driver):
     src, tgt, _ = pair0
     origin = np.array([-9.0, -9.0, -9.0])
     for voxel in (0.05, 0.02):
@@ -289,7 +289,7 @@ def _check_dense_correspondences(engine, b2, sd, budget, init=None, rel=1e-6, ga
 
 
 @pytest.mark.parametrize("budget", [0, 1, 2, 3, 6, 12, 30])
-def test_dense_map_correspondences_of_the_result_transform_are_bit_exact(engine, b2, pair0, budget):
+def test_dense_map_correspondences_of_the_result_transform_are_bit_exact(engine, b2, pair0, budget, dense_driver):
     """Every launch of the dense-map ICP step after the first searches from what a speculative pass with the
     PREVIOUS transform kept (b2_icp_dense.cuh); stopping the registration after `budget` steps exposes the search of
     that step, large early updates and small late ones alike."""
@@ -306,7 +306,7 @@ def test_dense_map_correspondences_of_the_result_transform_are_bit_exact(engine,
     _check_dense_correspondences(engine, b2, sd, budget, init=T0, rel=0.0)
 
 
-def test_dense_map_correspondences_with_more_queries_than_one_round(engine, b2, pair0):
+def test_dense_map_correspondences_with_more_queries_than_one_round(engine, b2, pair0, dense_driver):
     """A raw 49,152-pt source is more than the 148 x 190 queries the step kernel serves per round: the first round
     searches from the speculative pass, the second one takes the full path — both must agree with the oracle.  Also
     tiny sources (fewer queries than CTAs, than lanes of a warp)."""
@@ -320,7 +320,7 @@ def test_dense_map_correspondences_with_more_queries_than_one_round(engine, b2, 
 
 
 @pytest.mark.parametrize("seed", [0, 1])
-def test_dense_map_correspondences_on_lattice_clouds(engine, b2, seed):
+def test_dense_map_correspondences_on_lattice_clouds(engine, b2, seed, dense_driver):
     """Voxel centroids on a 1/16 m lattice and queries on the half-lattice (every coordinate exactly representable):
     distances tie exactly between two, four and eight voxels, queries sit exactly on voxel faces and neighbours lie
     at exactly the gate (rejected: d2 < r2 is strict) — under the identity, a lattice-preserving start and a generic
@@ -350,7 +350,7 @@ def test_map_capacity_error(engine, b2, pair0):
     engine.map_init(0.05, [-9.0, -9.0, -9.0], 0.05, 1 << 16)  # re-initialising recovers
 
 
-def test_slam_sequence_resident_mode(engine, b2):
+def test_slam_sequence_resident_mode(engine, b2, dense_driver):
     """Streaming scan->map ICP + fuse (BASELINE config 2/4 shape) against the oracle's resident twin."""
     from lidar_slam_b200 import synth
 
@@ -555,11 +555,11 @@ def test_deferred_results_equal_per_scan_results(engine, b2):
 
 
 @pytest.mark.parametrize("budget,rel", [(500, 1e-6), (57, 0.0)])
-def test_slam_sequence_long_iteration_budget_uses_loop_node(engine, b2, budget, rel):
-    """Iteration budgets above the chained-launch window run the tail of the A.3 loop as a CUDA-graph WHILE
-    node once the step is captured (third scan on): the reference default of 500 iterations must stop at
-    convergence exactly like the oracle, and with the convergence test disabled (rel = 0) the loop must run
-    every one of the 57 steps (40 chained + 17 loop-node trips)."""
+def test_slam_sequence_long_iteration_budget_uses_loop_node(engine, b2, budget, rel, dense_driver):
+    """Long iteration budgets under both launch schemes: the persistent launch simply loops longer; with chained
+    launches the budget above the 40-launch window runs as a CUDA-graph WHILE node once the step is captured (third
+    scan on).  The reference default of 500 iterations must stop at convergence exactly like the oracle, and with
+    the convergence test disabled (rel = 0) every one of the 57 steps must run (40 chained + 17 loop-node trips)."""
     from lidar_slam_b200 import synth
 
     scene = synth.make_corridor_scene(13, length=12.0)
