@@ -65,7 +65,8 @@ SCENE_SEED = 1000
 START_X = 20.0
 METRIC = "scans/s ICP+fuse (49k-pt scan->2M-pt map)"
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, `ncu --set full`
-# (profiles/r02/icp_dense_2M_spec_full_raw.csv; cold caches between replays)
+# (profiles/r02/icp_dense_2M_persistent_full_raw.csv: 759.8 KB for one persistent launch of 42 steps, i.e. per ICP step —
+# the unit `achieved` is counted in; the chained driver moved 773 KB per step, icp_dense_2M_spec_full_raw.csv)
 ICP_DENSE_TRAFFIC = int(os.environ.get("B2_BENCH_TRAFFIC", 0)) or None
 
 
@@ -473,6 +474,12 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
             eng.synchronize()
         return ev0.elapsed_time(ev1) * 1e3 / n
     us_per_launch = (scan_step_us(30) - scan_step_us(6)) / 24.0
+    # the same two figures with one launch per ICP step (B2_DENSE_DRIVER_CHAINED) instead of the persistent launch
+    eng.set_dense_driver("chained")
+    us_chained = (scan_step_us(30) - scan_step_us(6)) / 24.0
+    step30_chained = scan_step_us(30)
+    eng.set_dense_driver("persistent")
+    step30 = scan_step_us(30)
     cand = eng.stencil_candidates(sd, init)
     # SURVEY 8(d) compulsory lower bound: every distinct byte once = the queries + the distinct occupied map cells
     # under all 27-cell stencils + the sums
@@ -492,12 +499,21 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
     bytes_ext = bytes_8d + 27 * 16 * ns + 136 * 148
     peak, src = hbm_peak()
     achieved = bytes_8d / (us_per_launch * 1e-6) / 1e9
-    return {"bound": "hbm", "kernel": "icp_dense_kernel (p2p, brick-major dense map)", "achieved": round(achieved, 1),
+    return {"bound": "hbm", "kernel": "icp_dense_kernel<persistent> (p2p, brick-major dense map)", "achieved": round(achieved, 1),
             "peak": peak, "peak_source": src, "unit": "GB/s", "frac": round(achieved / peak, 4),
             "frac_extended": round(bytes_ext / (us_per_launch * 1e-6) / 1e9 / peak, 4),
             "traffic": ICP_DENSE_TRAFFIC_DEFAULT if ICP_DENSE_TRAFFIC is None else ICP_DENSE_TRAFFIC,
-            "us_per_launch": round(us_per_launch, 3), "us_per_launch_eager_chain": round(us_eager, 3),
+            "us_per_launch": round(us_per_launch, 3),
+            "launch_unit": "one ICP step: a trip of the loop of the persistent launch that runs a whole registration "
+                           "(b2_set_dense_driver: PERSISTENT, the default) — the unit the algorithmic bytes are counted for",
+            "us_per_registration_eager": round(us_eager * n_launch, 1), "steps_per_registration_eager": iters + 2,
             "launches_per_registration": round(n_launch, 1),
+            "chained_driver": {"us_per_launch": round(us_chained, 3), "scan_step_us_30_iterations": round(step30_chained, 1),
+                               "persistent_scan_step_us_30_iterations": round(step30, 1),
+                               "note": "B2_DENSE_DRIVER_CHAINED: one launch per ICP step, chained with programmatic "
+                                       "dependent launch; a step costs about the same either way, the persistent launch "
+                                       "saves the launches that only find the registration finished and the first / "
+                                       "last launch of the chain"},
             "queries": int(ns), "candidates": int(cand),
             "algorithmic_bytes_per_launch": int(bytes_8d), "algorithmic_bytes_extended": int(bytes_ext),
             "compulsory_bytes_per_launch": int(bytes_compulsory), "touched_map_voxels": touched,
@@ -506,15 +522,14 @@ def roofline_icp(eng, dev_scans, poses, torch, b2):
                                "nothing because the touched bricks stay L2-resident from launch to launch",
             "note": "us_per_launch = (scan step with a 30-iteration budget - scan step with a 6-iteration budget) / 24, "
                     "convergence test disabled, graph-replayed as in the timed region (CUDA events on the library's "
-                    "stream); us_per_launch_eager_chain = a registration launched eagerly / its launches.  Either way "
-                    "the figure is the duration of a chain of launches / launches, i.e. it includes the launch-to-launch "
-                    "dependency (fold of the previous partials + SE(3) solve + broadcast), which is most of it: a step "
-                    "is a chain of dependent latencies, not a bandwidth problem (measured DRAM traffic per launch is "
-                    "below the algorithmic bytes: the stencils of neighbouring queries overlap in L1/L2)"}
+                    "stream): the time one more ICP step adds.  It includes the step-to-step dependency (exchange and "
+                    "fold of the 148 partials + SE(3) solve + broadcast), which is most of it: a step is a chain of "
+                    "dependent latencies, not a bandwidth problem (measured DRAM traffic per step is below the "
+                    "algorithmic bytes: the stencils of neighbouring queries overlap in L1/L2)"}
 
 
 # traffic of the dense kernel from the committed ncu capture (bytes per launch); see profiles/README.md
-ICP_DENSE_TRAFFIC_DEFAULT = 773_100
+ICP_DENSE_TRAFFIC_DEFAULT = 18_100
 
 
 def run_batched(eng, args, rank, world, device, barrier, max_over_ranks, b2, b2batch):
