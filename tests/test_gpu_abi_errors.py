@@ -101,3 +101,27 @@ def test_scan_path_and_scan_downsample_arguments(raw, b2):
     assert lib.b2_scan_downsample(h, eng.pack(bad).data_ptr(), 500, 0.02, out.data_ptr(), C.byref(n)) == -4  # KEY_RANGE
     # the handle is usable again
     assert lib.b2_scan_downsample(h, pts.data_ptr(), 500, 0.02, out.data_ptr(), C.byref(n)) == 0 and 0 < n.value <= 500
+
+
+def test_dense_driver_switch_and_correspondence_report_arguments(raw, b2):
+    """b2_set_dense_driver / b2_map_icp_corr: unknown driver, NULL outputs, call before the map exists, and a slab map
+    (voxel edge < gate), which has no per-query match report."""
+    eng, lib, h = raw
+    assert lib.b2_set_dense_driver(h, 5) == INVALID and "driver" in _err(lib, h)
+    assert lib.b2_set_dense_driver(h, 1) == 0 and lib.b2_set_dense_driver(h, 0) == 0
+    pts = eng.pack(np.random.default_rng(5).uniform(-1, 1, size=(400, 3)).astype(np.float32))
+    prm, res = b2.make_params(0.05, 3), b2.IcpResult()
+    d2 = eng.empty(400, torch.float64)
+    match = eng.empty((400, 4), torch.float32)
+    rc = lib.b2_map_icp_corr(h, pts.data_ptr(), 400, None, C.byref(prm), C.byref(res), d2.data_ptr(), match.data_ptr())
+    assert rc == STATE  # no map yet
+    eng.map_init(0.05, [-2.0, -2.0, -2.0], 0.05, 1 << 14)
+    eng.map_fuse(pts)
+    assert lib.b2_map_icp_corr(h, pts.data_ptr(), 400, None, C.byref(prm), C.byref(res), None, match.data_ptr()) == INVALID
+    assert lib.b2_map_icp_corr(h, pts.data_ptr(), 0, None, C.byref(prm), C.byref(res), d2.data_ptr(), match.data_ptr()) == INVALID
+    assert lib.b2_map_icp_corr(h, pts.data_ptr(), 400, None, C.byref(prm), C.byref(res), d2.data_ptr(), match.data_ptr()) == 0
+    assert res.fitness > 0.9 and float(d2.max()) < 0.05 ** 2  # (nearly) every point is its own voxel's centroid
+    eng.map_init(0.02, [-2.0, -2.0, -2.0], 0.05, 1 << 14)  # slab map
+    eng.map_fuse(pts)
+    rc = lib.b2_map_icp_corr(h, pts.data_ptr(), 400, None, C.byref(prm), C.byref(res), d2.data_ptr(), match.data_ptr())
+    assert rc == INVALID and "brick-major" in _err(lib, h)
