@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
 #include <functional>
 
@@ -214,6 +215,17 @@ struct HintGuard {  // widen the radix pass budget for the duration of a call
 }  // namespace
 }  // namespace b2
 
+namespace b2 {
+namespace {
+std::atomic<int> g_live_handles[64];
+std::atomic<unsigned long long> g_handles_epoch{0};
+}  // namespace
+void handle_born(int device) { if (device >= 0 && device < 64) g_live_handles[device]++; g_handles_epoch++; }
+void handle_gone(int device) { if (device >= 0 && device < 64) g_live_handles[device]--; g_handles_epoch++; }
+int live_handles(int device) { return device >= 0 && device < 64 ? g_live_handles[device].load() : 2; }
+unsigned long long handles_epoch() { return g_handles_epoch.load(); }
+}  // namespace b2
+
 using namespace b2;
 
 static_assert(sizeof(b2_icp_result) == sizeof(IcpResultDev), "result layouts must match");
@@ -295,6 +307,7 @@ int b2_create(int device, b2_handle* out) {
         delete c;
         return B2_ERR_CUDA;
     }
+    handle_born(device);
     *out = reinterpret_cast<b2_handle>(c);
     return B2_OK;
 }
@@ -302,6 +315,7 @@ int b2_create(int device, b2_handle* out) {
 int b2_destroy(b2_handle h) {
     CTX(h);
     cudaStreamSynchronize(c->stream);
+    handle_gone(c->device);
     for (int i = 0; i < 2; ++i) {
         if (c->front_graph[i].exec) cudaGraphExecDestroy(c->front_graph[i].exec);
         if (c->main_graph[i].exec) cudaGraphExecDestroy(c->main_graph[i].exec);
@@ -964,7 +978,8 @@ static int run_graphed(Context* c, ScanGraph& sg, int n, double ds_voxel, const 
                        const b2_icp_params* params, const std::function<int()>& body) {
     static const bool no_graph = getenv("B2_NO_GRAPH") != nullptr;
     const bool same = sg.n == n && sg.ds_voxel == ds_voxel && sg.scan == scan && sg.passes_hint == c->sort_passes_hint &&
-                      std::memcmp(&sg.params, params, sizeof(*params)) == 0 && sg.generation == c->ws_generation;
+                      std::memcmp(&sg.params, params, sizeof(*params)) == 0 && sg.generation == c->ws_generation &&
+                      sg.handles_epoch == handles_epoch();
     if (no_graph) return body();
     if (same && sg.exec) {
         B2_CUDA_OK(c, cudaGraphLaunch(sg.exec, c->stream));
@@ -976,6 +991,7 @@ static int run_graphed(Context* c, ScanGraph& sg, int n, double ds_voxel, const 
         sg.exec = nullptr;
         B2_TRY(body());
         sg.n = n; sg.ds_voxel = ds_voxel; sg.scan = scan; sg.params = *params; sg.generation = c->ws_generation;
+        sg.handles_epoch = handles_epoch();
         sg.passes_hint = c->sort_passes_hint;
         return B2_OK;
     }

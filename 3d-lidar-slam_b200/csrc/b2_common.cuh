@@ -47,6 +47,13 @@ enum WsSlot : int {
 
 struct MapState;  // b2_map.cu
 
+// Handles alive on a device in this process.  The persistent dense-map registration wants every CTA of its grid
+// resident (one per SM); two such launches from two handles of one process could each hold part of the SMs and
+// wait for the rest, so the persistent driver is only taken while the handle is the only one on its device
+// (b2_api.cu keeps the count; a change invalidates the captured scan steps through `handles_epoch`).
+int live_handles(int device);
+unsigned long long handles_epoch();
+
 // Cached CUDA graph of one scan step (b2_api.cu) and the key it was captured for.
 struct ScanGraph {
     cudaGraphExec_t exec = nullptr;
@@ -55,6 +62,7 @@ struct ScanGraph {
     const void* scan = nullptr;
     b2_icp_params params{};
     unsigned long long generation = 0;
+    unsigned long long handles_epoch = 0;
     int kernel_nodes = 0;
     int passes_hint = 0;  // radix pass budget baked into the captured sorts
 };
