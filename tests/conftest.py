@@ -62,6 +62,9 @@ def dense_driver(request, engine):
     """Run a test under both launch schemes of a registration against the brick-major resident map
     (include/b2slam.h B2_DENSE_DRIVER_*): one persistent launch, or one launch per ICP step.  Same kernel body,
     identical results."""
+    import gc
+
+    gc.collect()  # (the persistent launch is only taken while this engine is the only live handle on the device)
     engine.set_dense_driver(request.param)
     yield request.param
     engine.set_dense_driver("persistent")

@@ -271,12 +271,16 @@ def test_map_icp_matches_oracle(engine, b2, pair0, driver, dense_driver):
         engine.map_icp(sd, b2.make_params(0.5, 30))
 
 
-def _check_dense_correspondences(engine, b2, sd, budget, init=None, rel=1e-6, gate=0.05):
+def _check_dense_correspondences(engine, b2, sd, budget, init=None, rel=1e-6, gate=0.05, driver=None):
     """The correspondence set of the last evaluated transform (the result's) of the dense-map step kernel versus the
     oracle's search with that very transform on the exported centroids: matched / unmatched, d2 and the matched
     voxel (ties -> lowest canonical index) bit for bit."""
     cent, _ = engine.map_export()
+    l0 = engine.launch_count()
     res, d2, match = engine.map_icp_corr(sd, b2.make_params(gate, budget, rel_fitness=rel, rel_rmse=rel), init=init)
+    if driver is not None and budget >= 6:  # the scheme asked for is the one that ran: 1 launch vs budget + 2
+        n_launch = engine.launch_count() - l0
+        assert (n_launch <= 5) == (driver == "persistent"), (driver, n_launch)
     tgt = f64(xyz(cent))
     oidx, od2 = orc.nn_search(orc.transform(f64(xyz(sd)), res.matrix()), tgt, gate)
     m = match.cpu().numpy()
@@ -297,7 +301,7 @@ def test_dense_map_correspondences_of_the_result_transform_are_bit_exact(engine,
     engine.map_init(0.05, [-9.0, -9.0, -9.0], 0.05, 1 << 18)
     engine.map_fuse(engine.pack(tgt))
     sd = _down(engine, src)
-    res, hit = _check_dense_correspondences(engine, b2, sd, budget, rel=0.0 if budget < 30 else 1e-6)
+    res, hit = _check_dense_correspondences(engine, b2, sd, budget, rel=0.0 if budget < 30 else 1e-6, driver=dense_driver)
     assert res.iterations == budget or budget == 30
     assert 0.3 < hit.mean() < 1.0  # matched and unmatched queries both occur
     # a start far from the answer: the first updates move queries across several cells
