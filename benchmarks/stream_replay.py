@@ -123,7 +123,12 @@ def main():
                     f"voxel {args.map_voxel} m, gate 0.05 m, <= {args.max_iteration} iterations, through "
                     f"B200ICPProcessor.construct_global_map (pageable host scans, pose read back every frame)",
         "preloaded_map_voxels": preloaded, "preload_s": round(t_pre, 1),
-        "scans_per_s_e2e": round(n / times.sum(), 1), "seconds": round(float(times.sum()), 3),
+        # the first three frames carry one-off costs (lazy kernel loading, workspace allocation, the eager run and the
+        # capture of the scan step's graphs): anything from 10 to several hundred ms depending on the box
+        "scans_per_s_e2e": round((n - 3) / times[3:].sum(), 1) if n > 6 else round(n / times.sum(), 1),
+        "seconds": round(float(times.sum()), 3),
+        "scans_per_s_wall_all_frames": round(n / times.sum(), 1),
+        "first_frames_ms": [round(float(t) * 1e3, 2) for t in times[:3]],
         "first_100_scans_per_s": round(h / times[5:5 + h].sum(), 1) if n > h + 5 else None,
         "last_100_scans_per_s": round(h / times[-h:].sum(), 1),
         "frame_us": {"median": round(float(np.median(times)) * 1e6, 1), "p99": round(float(np.percentile(times, 99)) * 1e6, 1),
