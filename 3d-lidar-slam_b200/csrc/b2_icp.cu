@@ -315,7 +315,8 @@ int icp_run(Context* c, const float4* src, int ns_max, const int* src_offsets, c
     dim3 g(gx, n_pairs);
     // the dense-map registration as ONE persistent launch (b2_set_dense_driver; every CTA of the grid must be resident)
     const bool dense_persist = dense && c->dense_driver == B2_DENSE_DRIVER_PERSISTENT && gx <= kCtasPerSm * kSMs &&
-                               live_handles(c->device) == 1;  // (see live_handles: two resident grids could starve each other)
+                               live_handles(c->device) == 1 &&  // (see live_handles: two resident grids could starve each other)
+                               prm.max_iter + 2 < 1024;          // (the partials' tags keep ten bits for the step)
     const int launches = search_only ? 1 : (dense_persist ? 1 : prm.max_iter + 1 + (dense ? 1 : 0));
 #ifdef B2_EXPERIMENTS
     // (opt-in: on B200 the software grid barrier + solve of a step costs more than a kernel boundary)
