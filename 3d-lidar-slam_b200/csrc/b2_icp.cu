@@ -19,7 +19,8 @@
 //   b2_icp_group.cuh    icp_iter_kernel: four lanes per query, probes in parallel (dense map, single pairs)
 //   b2_icp_sweep.cuh    icp_sweep_kernel: one thread per query, pruned walk (batches on pair / slab grids)
 //   b2_icp_dense.cuh    icp_dense_kernel: the streaming path (dense resident map): redundant fold + solve per CTA,
-//                       no ticket / last-CTA tail
+//                       no ticket / last-CTA tail, search from a speculative pass run beside the solve; by default ONE
+//                       persistent launch per registration whose CTAs exchange tagged partial sums (b2_set_dense_driver)
 //   b2_icp_persist.cuh  persistent driver — experiment, only built with -DB2_EXPERIMENTS (B2_EXPERIMENTS=1 build)
 //   this file           launchers, the driver choice, the chained-launch / WHILE-node loop (icp_run)
 //
